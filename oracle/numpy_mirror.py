@@ -1,0 +1,225 @@
+"""
+numpy_mirror.py — second, independent restatement (pure Python loops) of the reference's deposit
+loops, used ONLY to cross-check oracle/s2g_oracle.c on small cases.  TEST INFRASTRUCTURE.
+
+Follows: src/cic_interpolation/cic_2D.jl:11-244, cic_3D.jl:13-209, cic_shared.jl:9-121,
+src/healpix_interpolation/main.jl:143-213, pixel_weights.jl:6-140, constributing_pixels.jl:7-22.
+Written against the Julia text, not against the C file, so that a typo in one shows up as a diff.
+"""
+import math
+
+import numpy as np
+
+PI = math.pi
+
+
+def W(kernel, dim, u, h_inv):
+    """SPHKernels.jl v2 kernel values (third-party; shapes restated)."""
+    norms = {
+        "Cubic": {2: 40.0 / (7.0 * PI), 3: 8.0 / PI},
+        "Quintic": {2: 3 ** 7 * 7.0 / (478.0 * PI), 3: 3 ** 7 / (40.0 * PI)},
+        "WendlandC2": {2: 7.0 / PI, 3: 21.0 / (2.0 * PI)},
+        "WendlandC4": {2: 9.0 / PI, 3: 495.0 / (32.0 * PI)},
+        "WendlandC6": {2: 78.0 / (7.0 * PI), 3: 1365.0 / (64.0 * PI)},
+        "WendlandC8": {2: 8.0 / (3.0 * PI), 3: 357.0 / (64.0 * PI)},
+    }
+    n = norms[kernel][dim] * h_inv ** dim
+    if u >= 1.0:
+        return 0.0
+    if kernel == "Cubic":
+        w = 1.0 + 6.0 * (u - 1.0) * u ** 2 if u < 0.5 else 2.0 * (1.0 - u) ** 3
+    elif kernel == "Quintic":
+        w = (1 - u) ** 5 - 6 * max(2 / 3 - u, 0.0) ** 5 + 15 * max(1 / 3 - u, 0.0) ** 5
+    elif kernel == "WendlandC2":
+        w = (1 - u) ** 4 * (1 + 4 * u)
+    elif kernel == "WendlandC4":
+        w = (1 - u) ** 6 * (1 + 6 * u + 35 / 3 * u ** 2)
+    elif kernel == "WendlandC6":
+        w = (1 - u) ** 8 * (1 + 8 * u + 25 * u ** 2 + 32 * u ** 3)
+    elif kernel == "WendlandC8":
+        w = (1 - u) ** 10 * (5 + 50 * u + 210 * u ** 2 + 450 * u ** 3 + 429 * u ** 4)
+    else:
+        raise KeyError(kernel)
+    return w * n
+
+
+def _minmax(x, h, n):
+    return max(math.floor(x - h), 0), min(math.floor(x + h), n - 1)
+
+
+def _x_dx(x, h, i):
+    return x - i - 0.5, min(x + h, i + 1) - max(x - h, i)
+
+
+def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel, kdim=2, calc_mean=True):
+    pos = np.asarray(pos, float); binq = np.asarray(binq, float)
+    n = len(hsml)
+    nim = 1 if binq.ndim == 1 else binq.shape[1]
+    img = np.zeros((npix * npix, nim + 1))
+    for p in range(n):
+        bq = np.atleast_1d(binq[p])
+        allzero = bool(np.all(bq == 0))
+        if allzero and not calc_mean:
+            continue
+        h = hsml[p] * len2pix
+        hinv = 1.0 / h
+        area = (2 * h) ** 2
+        rr = rho[p] * (1.0 / (len2pix * len2pix * len2pix))
+        dz = m[p] / rr / area
+        x = pos[p, 0] * len2pix + 0.5 * npix
+        y = pos[p, 1] * len2pix + 0.5 * npix
+        i0, i1 = _minmax(x, h, npix)
+        j0, j1 = _minmax(y, h, npix)
+        wk = {}
+        A = {}
+        ndist = ntot = 0
+        dw = da = 0.0
+        for i in range(i0, i1 + 1):
+            xd, dx = _x_dx(x, h, i)
+            for j in range(j0, j1 + 1):
+                yd, dy = _x_dx(y, h, j)
+                u = math.sqrt(xd * xd + yd * yd) * hinv
+                dA = dx * dy
+                idx = i * npix + j
+                A[idx] = dA
+                da += dA
+                ntot += 1
+                if u <= 1:
+                    k = W(kernel, kdim, u, hinv)
+                    dw += k * dA
+                    ndist += 1
+                    wk[idx] = k
+                else:
+                    wk[idx] = 0.0
+        if dw == 0.0:
+            ndist = ntot
+            for key in wk:
+                wk[key] = 1.0
+            wpp = ndist / da if da != 0 else 1.0
+        else:
+            wpp = ndist / dw
+        if ndist == 0:
+            continue  # empty footprint: nothing to write (area/0 never used)
+        kn = area / ndist
+        an = kn * wpp * w[p] * dz
+        for idx in wk:
+            pw = wk[idx] * A[idx] * an
+            if pw != 0.0:
+                img[idx, nim] += pw
+                if allzero:
+                    img[idx, 0] += 0.0 * pw
+                else:
+                    for q in range(nim):
+                        img[idx, q] += bq[q] * pw
+    return img
+
+
+def cic_mapping_3d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel, kdim=3, calc_mean=False):
+    pos = np.asarray(pos, float)
+    n = len(hsml)
+    img = np.zeros((npix ** 3, 2))
+    for p in range(n):
+        bq = float(binq[p])
+        if bq == 0 and not calc_mean:
+            continue
+        h = hsml[p] * len2pix
+        hinv = 1.0 / h
+        rr = rho[p] / len2pix ** 3
+        vol = m[p] / rr
+        x = pos[p, 0] * len2pix + 0.5 * npix
+        y = pos[p, 1] * len2pix + 0.5 * npix
+        z = pos[p, 2] * len2pix + 0.5 * npix
+        i0, i1 = _minmax(x, h, npix)
+        j0, j1 = _minmax(y, h, npix)
+        k0, k1 = _minmax(z, h, npix)
+        wk = {}
+        V = {}
+        ndist = ntot = 0
+        dw = dv = 0.0
+        for i in range(i0, i1 + 1):
+            xd, dx = _x_dx(x, h, i)
+            for j in range(j0, j1 + 1):
+                yd, dy = _x_dx(y, h, j)
+                for k in range(k0, k1 + 1):
+                    zd, dzz = _x_dx(z, h, k)
+                    idx = i * npix * npix + j * npix + k
+                    dV = dx * dy * dzz
+                    u = math.sqrt(xd * xd + yd * yd + zd * zd) * hinv
+                    V[idx] = dV
+                    dv += dV
+                    ntot += 1
+                    if u <= 1:
+                        kk = W(kernel, kdim, u, hinv)
+                        dw += kk * dV
+                        ndist += 1
+                        wk[idx] = kk
+                    else:
+                        wk[idx] = 0.0
+        if dw == 0.0:
+            ndist = ntot
+            for key in wk:
+                wk[key] = 1.0
+            wpp = ndist / dv if dv != 0 else 1.0
+        else:
+            wpp = ndist / dw
+        if ndist == 0:
+            continue
+        kn = vol / ndist
+        vn = kn * wpp * w[p] * len2pix
+        for idx in wk:
+            pw = wk[idx] * V[idx] * vn
+            if pw != 0:
+                img[idx, 1] += pw
+                img[idx, 0] += bq * pw
+    return img
+
+
+# ------------------------------------------------------------------ HEALPix (RING), 0-based pixels
+def hp_ring_info(nside, ring):
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    if ring < nside:
+        return 2 * ring * (ring - 1), 4 * ring, True
+    if ring <= 3 * nside:
+        return ncap + (ring - nside) * 4 * nside, 4 * nside, ((ring - nside) & 1) == 0
+    nr = 4 * nside - ring
+    return npix - 2 * nr * (nr + 1), 4 * nr, True
+
+
+def hp_ring2z(nside, ring):
+    if ring < nside:
+        return 1.0 - ring * ring * (4.0 / (12 * nside * nside))
+    if ring <= 3 * nside:
+        return (2 * nside - ring) * (2 * nside * (4.0 / (12 * nside * nside)))
+    r = 4 * nside - ring
+    return r * r * (4.0 / (12 * nside * nside)) - 1.0
+
+
+def hp_pix_center(nside, pix):
+    """(z, phi) of a pixel centre from its ring/in-ring position — independent of pix2ang_ring's sqrt inversion."""
+    npix = 12 * nside * nside
+    ncap = 2 * nside * (nside - 1)
+    if pix < ncap:
+        ring = int((1 + math.isqrt(1 + 2 * pix)) // 2)
+    elif pix < npix - ncap:
+        ring = (pix - ncap) // (4 * nside) + nside
+    else:
+        r = int((1 + math.isqrt(2 * (npix - pix) - 1)) // 2)
+        ring = 4 * nside - r
+    start, nr, shifted = hp_ring_info(nside, ring)
+    iphi = pix - start  # 0-based in ring
+    phi = (iphi + (0.5 if shifted else 0.0)) * 2 * PI / nr
+    return hp_ring2z(nside, ring), phi, ring
+
+
+def hp_brute_disc(nside, theta, phi, radius):
+    """Brute force: all pixels whose centre is within `radius` of (theta,phi)."""
+    v = np.array([math.sin(theta) * math.cos(phi), math.sin(theta) * math.sin(phi), math.cos(theta)])
+    out = []
+    for pix in range(12 * nside * nside):
+        z, ph, _ = hp_pix_center(nside, pix)
+        s = math.sqrt(max(0.0, (1 - z) * (1 + z)))
+        c = np.array([s * math.cos(ph), s * math.sin(ph), z])
+        if math.acos(max(-1.0, min(1.0, float(v @ c)))) < radius:
+            out.append(pix)
+    return out
