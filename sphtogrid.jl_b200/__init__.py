@@ -1,0 +1,18 @@
+"""sphtogrid.jl_b200 — B200-native particle deposition behind SPHtoGrid.jl's API.
+
+Host mirror (same names as the Julia package) of the ONE hot path this project accelerates; every compute call goes
+through the C ABI of libsphtogrid_cuda.so (include/sphtogrid_cuda.h).  There is no CPU fallback.
+"""
+from ._lib import Context, S2GError, build, default_context, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
+from .kernels import (AbstractSPHKernel, Cubic, Quintic, WendlandC2, WendlandC4, WendlandC6,  # noqa: F401
+                      WendlandC8)
+from .parameters import mappingParameters, recentred_parameters  # noqa: F401
+from .mapping import (sphMapping, map_it, cic_mapping_2D, cic_mapping_3D, reduce_image_2D,  # noqa: F401
+                      reduce_image_3D, center_particles, filter_particles_in_image, domain_decomposition,
+                      part_weight_one, part_weight_physical, part_weight_emission, part_weight_spectroscopic)
+from .healpix import healpix_map, healpix_deposit, filter_sort_particles, find_in_shell  # noqa: F401
+from .stencils import cic_deposit, tsc_deposit  # noqa: F401
+from . import distributed  # noqa: F401
+
+__all__ = ["sphMapping", "map_it", "mappingParameters", "healpix_map", "Cubic", "Quintic", "WendlandC2", "WendlandC4",
+           "WendlandC6", "WendlandC8", "cic_deposit", "tsc_deposit", "Context"]

@@ -1,0 +1,295 @@
+// s2g_cic2d.cu — 2D Smac deposit, scatter strategy (warp per particle, red.global.add.f64), footprints,
+// reduce_image_2D epilogue and centre/filter kernels.
+//
+// Replaces: cic_mapping_2D (src/cic_interpolation/cic_2D.jl:103-244), calculate_weights (:11-72),
+//           reduce_image_2D (src/cic_interpolation/reduce_image.jl:8-31),
+//           center_particles / filter_particles_in_image (src/cic_interpolation/filter_shift.jl:6-67).
+#include "s2g_cic2d.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// one warp deposits one particle: pass A (weight sums) + pass B (normalised scatter)
+// lanes are laid out W wide along j (the contiguous image axis, indices.jl:6-8) and 32/W rows deep,
+// W = next power of two >= footprint width (capped at 32) so that small footprints still fill the warp.
+// ------------------------------------------------------------------------------------------------
+template <int KID>
+__device__ __forceinline__ void warp_deposit_2d(const Rec2& r, const s2g_particles& P, const s2g_geom& G, long long p,
+                                                int lane, double* __restrict__ image, unsigned long long& touched,
+                                                unsigned long long& fallback)
+{
+    const int ni = r.iMax - r.iMin + 1, nj = r.jMax - r.jMin + 1;
+    const int lw = nj >= 32 ? 5 : (nj <= 1 ? 0 : 32 - __clz(nj - 1));
+    const int W = 1 << lw, R = 32 >> lw;
+    const int c0 = lane & (W - 1), r0 = lane >> lw;
+
+    const double dx_lo = overlap_1d(r.x, r.h, r.iMin), dx_hi = overlap_1d(r.x, r.h, r.iMax);
+    const double dy_lo = overlap_1d(r.y, r.h, r.jMin), dy_hi = overlap_1d(r.y, r.h, r.jMax);
+
+    // ---- pass A: distr_weight = Σ wk·dA over pixels whose centre is inside the kernel, n_distr_pix
+    double sw = 0.0;
+    int cnt = 0;
+    for (int jc = c0; jc < nj; jc += W) {
+        const int j = r.jMin + jc;
+        const double yd = center_dist(r.y, (double)j);
+        const double yd2 = __dmul_rn(yd, yd);
+        const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+        for (int ir = r0; ir < ni; ir += R) {
+            const int i = r.iMin + ir;
+            const double xd = center_dist(r.x, (double)i);
+            const double u = u_of(__dmul_rn(xd, xd), yd2, r.hinv);
+            if (u <= 1.0) {
+                const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                sw = fma(kernel_shape<KID>(u), dx * dy, sw);
+                ++cnt;
+            }
+        }
+    }
+    sw = warp_sum(sw);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+
+    // ---- normalisation (cic_2D.jl:51-69, :187-188)
+    bool fb = false;
+    double n_distr, wpp;
+    if (sw == 0.0) {
+        fb = true;
+        double da = 0.0;
+        for (int jc = c0; jc < nj; jc += W) {
+            const int j = r.jMin + jc;
+            const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+            for (int ir = r0; ir < ni; ir += R) {
+                const int i = r.iMin + ir;
+                const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                da += dx * dy;
+            }
+        }
+        da = warp_sum(da);
+        n_distr = (double)ni * (double)nj;
+        wpp = (da != 0.0) ? n_distr / da : 1.0;
+        if (lane == 0) ++fallback;
+    } else {
+        n_distr = (double)cnt;
+        wpp = n_distr / sw;
+    }
+    const double kernel_norm = r.area / n_distr;
+    const double area_norm = kernel_norm * wpp * r.w * r.dz;
+
+    // ---- pass B: pix_weight = wk·A·area_norm; update_image! (cic_shared.jl:111-121)
+    const long long npl = G.npix * G.npix;
+    double* __restrict__ wplane = image + npl * G.n_images;
+    const int nim = G.n_images;
+    double q0 = 0.0;
+    if (!r.all_zero && nim == 1) q0 = ld_in(P.binq, p, P.in_dtype);
+    for (int jc = c0; jc < nj; jc += W) {
+        const int j = r.jMin + jc;
+        const double yd = center_dist(r.y, (double)j);
+        const double yd2 = __dmul_rn(yd, yd);
+        const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+        for (int ir = r0; ir < ni; ir += R) {
+            const int i = r.iMin + ir;
+            const double xd = center_dist(r.x, (double)i);
+            double wk;
+            if (fb)
+                wk = 1.0;
+            else {
+                const double u = u_of(__dmul_rn(xd, xd), yd2, r.hinv);
+                if (!(u <= 1.0)) continue;
+                wk = kernel_shape<KID>(u);
+            }
+            const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+            const double pw = wk * (dx * dy) * area_norm;
+            if (pw != 0.0) {
+                const long long idx = (long long)i * G.npix + j;
+                red_add(wplane + idx, pw);
+                if (r.all_zero) {
+                    if (!isfinite(pw)) red_add(image + idx, 0.0 * pw);  // bin_q collapsed to 0.0 (cic_2D.jl:160-162)
+                } else if (nim == 1) {
+                    red_add(image + idx, q0 * pw);
+                } else {
+                    for (int q = 0; q < nim; ++q)
+                        red_add(image + npl * q + idx, ld_in(P.binq, (long long)nim * p + q, P.in_dtype) * pw);
+                }
+                ++touched;
+            }
+        }
+    }
+}
+
+// particle list: either all particles [0,n) (list == nullptr) or an explicit index list (scatter bin of AUTO)
+template <int KID>
+__global__ void __launch_bounds__(256) k_scatter2d(s2g_particles P, s2g_geom G, const int* __restrict__ list,
+                                                   long long n_list, double* __restrict__ image,
+                                                   unsigned long long* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
+    constexpr int CHUNK = 4;
+    for (;;) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_list) break;
+        const long long end = min(base + CHUNK, n_list);
+        for (long long t = base; t < end; ++t) {
+            const long long p = list ? (long long)list[t] : t;
+            Rec2 r;
+            if (!make_rec2(P, G, p, r)) continue;
+            if (lane == 0) {
+                ++mapped;
+                fpx += (unsigned long long)(r.iMax - r.iMin + 1) * (unsigned long long)(r.jMax - r.jMin + 1);
+            }
+            warp_deposit_2d<KID>(r, P, G, p, lane, image, touched, fallback);
+        }
+    }
+    touched = (unsigned long long)warp_sum_ll((long long)touched);
+    if (lane == 0) {
+        if (touched) atomicAdd(&counters[CNT_TOUCHED], touched);
+        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
+        if (mapped) atomicAdd(&counters[CNT_MAPPED], mapped);
+        if (mapped) atomicAdd(&counters[CNT_SCATTER], mapped);
+        if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
+    }
+}
+
+template <int KID>
+static int launch_scatter2d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list,
+                              long long n_list, double* image)
+{
+    if (n_list <= 0) return S2G_OK;
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    const int warps_needed = (int)std::min<long long>((n_list + 3) / 4, (long long)ctx->sm_count * 8 * 8);
+    int blocks = max(1, (warps_needed + 7) / 8);
+    blocks = min(blocks, ctx->sm_count * 8);
+    k_scatter2d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}
+
+int s2g_launch_scatter_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const int* list,
+                          long long n_list, double* image)
+{
+    switch (kernel) {
+    case S2G_KERNEL_CUBIC: return launch_scatter2d_k<S2G_KERNEL_CUBIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_QUINTIC: return launch_scatter2d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C2: return launch_scatter2d_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C4: return launch_scatter2d_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C6: return launch_scatter2d_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C8: return launch_scatter2d_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, G, list, n_list, image);
+    }
+    s2g_set_error("unknown kernel id %d", kernel);
+    return S2G_EINVAL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// footprints (bit-exact contract)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_footprints2d(s2g_particles P, s2g_geom G, long long* __restrict__ out)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const double px = ld_pos(P, p, 0), py = ld_pos(P, p, 1);
+    const double h = __dmul_rn(ld_in(P.hsml, p, P.in_dtype), G.len2pix);
+    const double x = __dadd_rn(__dmul_rn(px, G.len2pix), G.half_n);
+    const double y = __dadd_rn(__dmul_rn(py, G.len2pix), G.half_n);
+    const int n1 = (int)G.npix - 1;
+    out[4 * p + 0] = max(floor_to_int(__dadd_rn(x, -h)), 0);
+    out[4 * p + 1] = min(floor_to_int(__dadd_rn(x, h)), n1);
+    out[4 * p + 2] = max(floor_to_int(__dadd_rn(y, -h)), 0);
+    out[4 * p + 3] = min(floor_to_int(__dadd_rn(y, h)), n1);
+}
+
+__global__ void k_footprints3d(s2g_particles P, s2g_geom G, long long* __restrict__ out)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const double h = __dmul_rn(ld_in(P.hsml, p, P.in_dtype), G.len2pix);
+    const int n1 = (int)G.npix - 1;
+    for (int d = 0; d < 3; ++d) {
+        const double x = __dadd_rn(__dmul_rn(ld_pos(P, p, d), G.len2pix), G.half_n);
+        out[6 * p + 2 * d + 0] = max(floor_to_int(__dadd_rn(x, -h)), 0);
+        out[6 * p + 2 * d + 1] = min(floor_to_int(__dadd_rn(x, h)), n1);
+    }
+}
+
+int s2g_launch_footprints(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int dims, long long* out)
+{
+    if (P.n <= 0) return S2G_OK;
+    const int blocks = (int)((P.n + 255) / 256);
+    if (dims == 2)
+        k_footprints2d<<<blocks, 256, 0, ctx->stream>>>(P, G, out);
+    else
+        k_footprints3d<<<blocks, 256, 0, ctx->stream>>>(P, G, out);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce_image_2D: out[ix + nx*iy + nx*ny*q] = image[ix*nx + iy, q] (/ weight where reduce && weight > 0)
+// = divide + transpose; 32x32 tiles through padded shared memory, both sides coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce2d(const double* __restrict__ image, long long nx, long long ny,
+                                                  int n_images, int reduce_image, double* __restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const long long npl = nx * ny;
+    const long long bx = blockIdx.x * 32LL, by = blockIdx.y * 32LL;  // bx: iy block (fast axis of flat), by: ix block
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
+    const double* __restrict__ wpl = image + npl * n_images;
+    for (int q = 0; q < n_images; ++q) {
+        const double* __restrict__ src = image + npl * q;
+        for (int r = ty; r < 32; r += 8) {
+            const long long ix = by + r, iy = bx + tx;
+            if (ix < nx && iy < ny) {
+                const long long k = ix * nx + iy;
+                double v = src[k];
+                if (reduce_image) {
+                    const double wv = wpl[k];
+                    if (wv > 0.0) v = v / wv;
+                }
+                tile[r][tx] = v;
+            }
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const long long iy = bx + r, ix = by + tx;
+            if (ix < nx && iy < ny) out[ix + nx * iy + npl * q] = tile[tx][r];
+        }
+        __syncthreads();
+    }
+}
+
+int s2g_launch_reduce_2d(s2g_ctx* ctx, const double* image, long long nx, long long ny, int n_images, int reduce_image,
+                         double* out)
+{
+    dim3 grid((unsigned)((ny + 31) / 32), (unsigned)((nx + 31) / 32));
+    k_reduce2d<<<grid, 256, 0, ctx->stream>>>(image, nx, ny, n_images, reduce_image, out);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// center_particles + filter_particles_in_image as a standalone pass (the fused path does both on the fly)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_center_filter(s2g_particles P, void* __restrict__ pos_out, uint8_t* __restrict__ mask)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const double x = ld_pos(P, p, 0), y = ld_pos(P, p, 1), z = ld_pos(P, p, 2);
+    if (pos_out) {
+        if (P.in_dtype == S2G_F64) {
+            double* o = reinterpret_cast<double*>(pos_out) + 3 * p;
+            o[0] = x; o[1] = y; o[2] = z;
+        } else {
+            float* o = reinterpret_cast<float*>(pos_out) + 3 * p;
+            o[0] = (float)x; o[1] = (float)y; o[2] = (float)z;  // exact: values are Float32-representable
+        }
+    }
+    if (mask) mask[p] = in_image(P, x, y, z) ? 1 : 0;
+}
+
+int s2g_launch_center_filter(s2g_ctx* ctx, const s2g_particles& P, void* pos_out, uint8_t* mask)
+{
+    if (P.n <= 0) return S2G_OK;
+    const int blocks = (int)((P.n + 255) / 256);
+    k_center_filter<<<blocks, 256, 0, ctx->stream>>>(P, pos_out, mask);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}

@@ -1,0 +1,84 @@
+// s2g_cic2d.cuh — per-particle pixel-space record of the 2D Smac deposit and the exact (bit-for-bit)
+// footprint arithmetic shared by the scatter and gather kernels.
+#pragma once
+#include "s2g_common.cuh"
+
+#ifdef __CUDACC__
+struct Rec2 {
+    double x, y;        // pixel coordinates (get_xyz, cic_shared.jl:85-100)
+    double h, hinv;     // hsml in pixels and its inverse (get_quantities_2D, cic_2D.jl:80-91)
+    double area;        // (2h)^2
+    double dz;          // m / rho_pix / area
+    double w;           // los weight
+    int iMin, iMax, jMin, jMax;  // pix_index_min_max (cic_shared.jl:46-52)
+    bool all_zero;      // bin_q == 0 for every image
+};
+
+// floor(Integer, v) clamped to int range (npix < 2^31 is enforced by the API)
+__device__ __forceinline__ int floor_to_int(double v)
+{
+    long long f = __double2ll_rd(v);
+    f = f < -2147483647LL ? -2147483647LL : f;
+    f = f > 2147483647LL ? 2147483647LL : f;
+    return (int)f;
+}
+
+// Builds the record of particle p.  Returns false when the particle does not deposit anything:
+//   - bin_q == 0 (all images) and !calc_mean          (cic_2D.jl:166)
+//   - fused sphMapping filter rejects its centre       (filter_shift.jl:50-58)
+//   - its clipped footprint is empty                   (loops iMin:iMax / jMin:jMax do not execute)
+// No FMA contraction anywhere on the path to the integer bounds: __dmul_rn/__dadd_rn are never fused.
+__device__ __forceinline__ bool make_rec2(const s2g_particles& P, const s2g_geom& G, long long p, Rec2& r)
+{
+    bool all_zero = true;
+    for (int q = 0; q < G.n_images; ++q)
+        if (ld_in(P.binq, (long long)G.n_images * p + q, P.in_dtype) != 0.0) all_zero = false;
+    if (all_zero && !G.calc_mean) return false;
+    r.all_zero = all_zero;
+
+    const double px = ld_pos(P, p, 0), py = ld_pos(P, p, 1);
+    if (P.fuse_center) {
+        const double pz = ld_pos(P, p, 2);
+        if (!in_image(P, px, py, pz)) return false;
+    }
+    const double hs = ld_in(P.hsml, p, P.in_dtype);
+    const double mm = ld_in(P.m, p, P.in_dtype);
+    const double rh = ld_in(P.rho, p, P.in_dtype);
+    r.w = ld_in(P.w, p, P.in_dtype);
+
+    r.h = __dmul_rn(hs, G.len2pix);
+    r.hinv = __ddiv_rn(1.0, r.h);
+    const double h2 = __dmul_rn(2.0, r.h);
+    r.area = __dmul_rn(h2, h2);
+    const double rho_p = __dmul_rn(rh, G.inv_l3);
+    r.dz = __ddiv_rn(__ddiv_rn(mm, rho_p), r.area);
+
+    r.x = __dadd_rn(__dmul_rn(px, G.len2pix), G.half_n);
+    r.y = __dadd_rn(__dmul_rn(py, G.len2pix), G.half_n);
+
+    const int n1 = (int)G.npix - 1;
+    r.iMin = max(floor_to_int(__dadd_rn(r.x, -r.h)), 0);
+    r.iMax = min(floor_to_int(__dadd_rn(r.x, r.h)), n1);
+    r.jMin = max(floor_to_int(__dadd_rn(r.y, -r.h)), 0);
+    r.jMax = min(floor_to_int(__dadd_rn(r.y, r.h)), n1);
+    return (r.iMin <= r.iMax) && (r.jMin <= r.jMax);
+}
+
+// get_dxyz (cic_shared.jl:60-62): overlap length of [x-h, x+h] with pixel [i, i+1]
+__device__ __forceinline__ double overlap_1d(double x, double h, int i)
+{
+    const double a = __dadd_rn(x, h), b = (double)(i + 1);
+    const double c = __dadd_rn(x, -h), d = (double)i;
+    return __dadd_rn(fmin(a, b), -fmax(c, d));
+}
+
+// x - i - 0.5 evaluated left to right (get_x_dx, cic_shared.jl:73)
+__device__ __forceinline__ double center_dist(double x, double id) { return __dadd_rn(__dadd_rn(x, -id), -0.5); }
+
+// u = sqrt(dx*dx + dy*dy) * hinv  (get_d_hsml, distances.jl:6-8), every operation individually rounded so that
+// the classification u <= 1 agrees with the reference for every pixel.
+__device__ __forceinline__ double u_of(double xd2, double yd2, double hinv)
+{
+    return __dmul_rn(__dsqrt_rn(__dadd_rn(xd2, yd2)), hinv);
+}
+#endif

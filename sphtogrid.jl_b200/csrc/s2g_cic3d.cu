@@ -1,0 +1,234 @@
+// s2g_cic3d.cu — 3D Smac deposit (scatter strategy) and reduce_image_3D epilogue.
+//
+// Replaces: cic_mapping_3D (src/cic_interpolation/cic_3D.jl:110-209), calculate_weights (:13-78),
+//           get_quantities_3D (:87-97), reduce_image_3D (src/cic_interpolation/reduce_image.jl:39-55).
+#include "s2g_cic2d.cuh"
+
+struct Rec3 {
+    double x, y, z, h, hinv, vol, w, q;
+    int lo[3], hi[3];
+};
+
+__device__ __forceinline__ bool make_rec3(const s2g_particles& P, const s2g_geom& G, long long p, Rec3& r)
+{
+    r.q = ld_in(P.binq, p, P.in_dtype);
+    if (r.q == 0.0 && !G.calc_mean) return false;  // cic_3D.jl:142
+    const double px = ld_pos(P, p, 0), py = ld_pos(P, p, 1), pz = ld_pos(P, p, 2);
+    if (P.fuse_center && !in_image(P, px, py, pz)) return false;
+    const double hs = ld_in(P.hsml, p, P.in_dtype);
+    const double mm = ld_in(P.m, p, P.in_dtype);
+    const double rh = ld_in(P.rho, p, P.in_dtype);
+    r.w = ld_in(P.w, p, P.in_dtype);
+    r.h = __dmul_rn(hs, G.len2pix);
+    r.hinv = __ddiv_rn(1.0, r.h);
+    r.vol = __ddiv_rn(mm, __ddiv_rn(rh, G.l3));
+    r.x = __dadd_rn(__dmul_rn(px, G.len2pix), G.half_n);
+    r.y = __dadd_rn(__dmul_rn(py, G.len2pix), G.half_n);
+    r.z = __dadd_rn(__dmul_rn(pz, G.len2pix), G.half_n);
+    const int n1 = (int)G.npix - 1;
+    const double c[3] = {r.x, r.y, r.z};
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r.lo[d] = max(floor_to_int(__dadd_rn(c[d], -r.h)), 0);
+        r.hi[d] = min(floor_to_int(__dadd_rn(c[d], r.h)), n1);
+        ok = ok && (r.lo[d] <= r.hi[d]);
+    }
+    return ok;
+}
+
+// lanes: W wide along k (contiguous axis, indices.jl:15-17), 32/W deep along j; i is looped by the whole warp
+template <int KID>
+__device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G, int lane,
+                                                double* __restrict__ image, unsigned long long& touched,
+                                                unsigned long long& fallback)
+{
+    const int ni = r.hi[0] - r.lo[0] + 1, nj = r.hi[1] - r.lo[1] + 1, nk = r.hi[2] - r.lo[2] + 1;
+    const int lw = nk >= 32 ? 5 : (nk <= 1 ? 0 : 32 - __clz(nk - 1));
+    const int W = 1 << lw, R = 32 >> lw;
+    const int c0 = lane & (W - 1), r0 = lane >> lw;
+
+    const double dx_lo = overlap_1d(r.x, r.h, r.lo[0]), dx_hi = overlap_1d(r.x, r.h, r.hi[0]);
+    const double dy_lo = overlap_1d(r.y, r.h, r.lo[1]), dy_hi = overlap_1d(r.y, r.h, r.hi[1]);
+    const double dz_lo = overlap_1d(r.z, r.h, r.lo[2]), dz_hi = overlap_1d(r.z, r.h, r.hi[2]);
+
+    double sw = 0.0;
+    int cnt = 0;
+    for (int kc = c0; kc < nk; kc += W) {
+        const int k = r.lo[2] + kc;
+        const double zd = center_dist(r.z, (double)k);
+        const double zd2 = __dmul_rn(zd, zd);
+        const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
+        for (int jr = r0; jr < nj; jr += R) {
+            const int j = r.lo[1] + jr;
+            const double yd = center_dist(r.y, (double)j);
+            const double yd2 = __dmul_rn(yd, yd);
+            const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
+            for (int ii = 0; ii < ni; ++ii) {
+                const int i = r.lo[0] + ii;
+                const double xd = center_dist(r.x, (double)i);
+                // sqrt(dx*dx + dy*dy + dz*dz) * hinv, left to right (distances.jl:15-17)
+                const double s = __dadd_rn(__dadd_rn(__dmul_rn(xd, xd), yd2), zd2);
+                const double u = __dmul_rn(__dsqrt_rn(s), r.hinv);
+                if (u <= 1.0) {
+                    const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
+                    sw = fma(kernel_shape<KID>(u), dx * dy * dz, sw);
+                    ++cnt;
+                }
+            }
+        }
+    }
+    sw = warp_sum(sw);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+
+    bool fb = false;
+    double n_distr, wpp;
+    if (sw == 0.0) {  // cic_3D.jl:57-72
+        fb = true;
+        double dv = 0.0;
+        for (int kc = c0; kc < nk; kc += W) {
+            const int k = r.lo[2] + kc;
+            const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
+            for (int jr = r0; jr < nj; jr += R) {
+                const int j = r.lo[1] + jr;
+                const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
+                for (int ii = 0; ii < ni; ++ii) {
+                    const int i = r.lo[0] + ii;
+                    const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
+                    dv += dx * dy * dz;
+                }
+            }
+        }
+        dv = warp_sum(dv);
+        n_distr = (double)ni * (double)nj * (double)nk;
+        wpp = (dv != 0.0) ? n_distr / dv : 1.0;
+        if (lane == 0) ++fallback;
+    } else {
+        n_distr = (double)cnt;
+        wpp = n_distr / sw;
+    }
+    const double kernel_norm = r.vol / n_distr;                       // cic_3D.jl:168
+    const double volume_norm = kernel_norm * wpp * r.w * G.len2pix;   // :169
+
+    const long long n = G.npix, npl = n * n * n;
+    for (int kc = c0; kc < nk; kc += W) {
+        const int k = r.lo[2] + kc;
+        const double zd = center_dist(r.z, (double)k);
+        const double zd2 = __dmul_rn(zd, zd);
+        const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
+        for (int jr = r0; jr < nj; jr += R) {
+            const int j = r.lo[1] + jr;
+            const double yd = center_dist(r.y, (double)j);
+            const double yd2 = __dmul_rn(yd, yd);
+            const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
+            for (int ii = 0; ii < ni; ++ii) {
+                const int i = r.lo[0] + ii;
+                const double xd = center_dist(r.x, (double)i);
+                double wk;
+                if (fb)
+                    wk = 1.0;
+                else {
+                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(xd, xd), yd2), zd2);
+                    const double u = __dmul_rn(__dsqrt_rn(s), r.hinv);
+                    if (!(u <= 1.0)) continue;
+                    wk = kernel_shape<KID>(u);
+                }
+                const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
+                const double pw = wk * (dx * dy * dz) * volume_norm;
+                if (pw != 0.0) {
+                    const long long idx = (long long)i * n * n + (long long)j * n + k;  // indices.jl:15-17
+                    red_add(image + npl + idx, pw);
+                    red_add(image + idx, r.q * pw);
+                    ++touched;
+                }
+            }
+        }
+    }
+}
+
+template <int KID>
+__global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, double* __restrict__ image,
+                                                   unsigned long long* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
+    constexpr int CHUNK = 4;
+    for (;;) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= P.n) break;
+        const long long end = min(base + CHUNK, P.n);
+        for (long long p = base; p < end; ++p) {
+            Rec3 r;
+            if (!make_rec3(P, G, p, r)) continue;
+            if (lane == 0) {
+                ++mapped;
+                fpx += (unsigned long long)(r.hi[0] - r.lo[0] + 1) * (unsigned long long)(r.hi[1] - r.lo[1] + 1) *
+                       (unsigned long long)(r.hi[2] - r.lo[2] + 1);
+            }
+            warp_deposit_3d<KID>(r, G, lane, image, touched, fallback);
+        }
+    }
+    touched = (unsigned long long)warp_sum_ll((long long)touched);
+    if (lane == 0) {
+        if (touched) atomicAdd(&counters[CNT_TOUCHED], touched);
+        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
+        if (mapped) atomicAdd(&counters[CNT_MAPPED], mapped);
+        if (mapped) atomicAdd(&counters[CNT_SCATTER], mapped);
+        if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
+    }
+}
+
+template <int KID>
+static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double* image)
+{
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    const int warps_needed = (int)std::min<long long>((P.n + 3) / 4, (long long)ctx->sm_count * 8 * 8);
+    int blocks = max(1, (warps_needed + 7) / 8);
+    blocks = min(blocks, ctx->sm_count * 8);
+    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, image, ctx->d_counters);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}
+
+int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image)
+{
+    if (P.n <= 0) return S2G_OK;
+    switch (kernel) {
+    case S2G_KERNEL_CUBIC: return launch_scatter3d_k<S2G_KERNEL_CUBIC>(ctx, P, G, image);
+    case S2G_KERNEL_QUINTIC: return launch_scatter3d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, image);
+    case S2G_KERNEL_WENDLAND_C2: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, G, image);
+    case S2G_KERNEL_WENDLAND_C4: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, G, image);
+    case S2G_KERNEL_WENDLAND_C6: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, G, image);
+    case S2G_KERNEL_WENDLAND_C8: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, G, image);
+    }
+    s2g_set_error("unknown kernel id %d", kernel);
+    return S2G_EINVAL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce_image_3D: same memory order as the flat buffer; divide gated on the QUANTITY plane (reduce_image.jl:49-51);
+// !reduce_image means the weight plane was overwritten with 1 (cic_interpolation.jl:230-232)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_reduce3d(const double* __restrict__ image, long long ncell, int reduce_image, double* __restrict__ out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < ncell; e += stride) {
+        double v = image[e];
+        if (v > 0.0) {
+            const double wv = reduce_image ? image[e + ncell] : 1.0;
+            v = v / wv;
+        }
+        out[e] = v;
+    }
+}
+
+int s2g_launch_reduce_3d(s2g_ctx* ctx, const double* image, long long npix, int reduce_image, double* out)
+{
+    const long long ncell = npix * npix * npix;
+    const int blocks = (int)std::min<long long>((ncell + 255) / 256, (long long)ctx->sm_count * 16);
+    k_reduce3d<<<max(blocks, 1), 256, 0, ctx->stream>>>(image, ncell, reduce_image, out);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}

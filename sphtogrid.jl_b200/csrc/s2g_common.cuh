@@ -1,0 +1,229 @@
+// s2g_common.cuh — shared declarations of libsphtogrid_cuda.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "sphtogrid_cuda.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+void s2g_set_error(const char* fmt, ...);
+
+#define S2G_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            s2g_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (_e == cudaErrorMemoryAllocation) ? S2G_ENOMEM : S2G_ECUDA;                      \
+        }                                                                                           \
+    } while (0)
+
+#define S2G_CHECK(cond, code, ...)                                                                  \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            s2g_set_error(__VA_ARGS__);                                                             \
+            return (code);                                                                          \
+        }                                                                                           \
+    } while (0)
+
+#define S2G_TRY(expr)                                                                               \
+    do {                                                                                            \
+        int _rc = (expr);                                                                           \
+        if (_rc != S2G_OK) return _rc;                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context: one device, one stream, a grow-only workspace arena (no cudaMalloc on the steady-state path)
+// ------------------------------------------------------------------------------------------------
+struct s2g_buffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct s2g_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int strategy = S2G_STRATEGY_AUTO;
+    s2g_stats stats{};
+    long long host_pairs = 0;  // (tile,particle) pairs of the gather path, counted on the host
+    std::map<std::string, s2g_buffer> pool;  // named scratch buffers, grow-only
+    cudaEvent_t ev[10]{};
+    // device-side counters (footprint pixels, touched, fallback, mapped, pairs ...)
+    unsigned long long* d_counters = nullptr;  // 16 x u64
+    unsigned long long* h_counters = nullptr;  // pinned mirror
+};
+
+// returns a device scratch buffer of at least `bytes` (contents undefined); keeps it for reuse
+int s2g_scratch(s2g_ctx* ctx, const char* name, size_t bytes, void** out);
+
+enum {
+    CNT_MAPPED = 0,
+    CNT_FOOTPRINT = 1,
+    CNT_TOUCHED = 2,
+    CNT_FALLBACK = 3,
+    CNT_PAIRS = 4,
+    CNT_SCATTER = 5,
+    CNT_GATHER = 6,
+    CNT_WORK = 7,  // dynamic work-queue cursor
+    CNT_N = 16
+};
+
+// ------------------------------------------------------------------------------------------------
+// geometry handed to the kernels
+// ------------------------------------------------------------------------------------------------
+struct s2g_geom {
+    double len2pix;     // par.len2pix
+    double inv_l3;      // 1/(len2pix*len2pix*len2pix)   (cic_2D.jl:86)
+    double l3;          // (len2pix*len2pix)*len2pix      (cic_3D.jl:93)
+    double half_n;      // 0.5*Npixels                    (cic_shared.jl:94-96)
+    long long npix;     // Npixels[1] == [2] == [3]
+    int n_images;
+    int calc_mean;
+};
+
+// particle inputs as handed over the ABI (device pointers)
+struct s2g_particles {
+    const void* pos;   // 3 x N interleaved
+    const void* hsml;
+    const void* m;
+    const void* rho;
+    const void* binq;  // n_images x N
+    const void* w;
+    long long n;
+    int in_dtype;      // S2G_F32 / S2G_F64
+    // optional fused centre+filter (sphMapping path); when active, positions are shifted in the INPUT precision
+    int fuse_center;   // 0/1
+    int periodic;
+    double shift[3];
+    double boxsize;
+    double halfsize[3];
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double ld_as_f64(const void* p, long long i)
+{
+    return (double)__ldg(reinterpret_cast<const T*>(p) + i);
+}
+
+__device__ __forceinline__ double ld_in(const void* p, long long i, int dtype)
+{
+    return dtype == S2G_F64 ? __ldg(reinterpret_cast<const double*>(p) + i)
+                            : (double)__ldg(reinterpret_cast<const float*>(p) + i);
+}
+
+// position component with the optional fused recentring of center_particles (filter_shift.jl:6-32):
+// the subtraction is evaluated in Float64 and ROUNDED BACK to the storage type (Float32 stays Float32).
+__device__ __forceinline__ double ld_pos(const s2g_particles& P, long long p, int d)
+{
+    if (P.in_dtype == S2G_F64) {
+        double v = __ldg(reinterpret_cast<const double*>(P.pos) + 3 * p + d);
+        if (P.fuse_center) {
+            v = __dadd_rn(v, -P.shift[d]);
+            if (P.periodic) {
+                double hb = P.boxsize / 2;
+                if (fabs(v) > hb) v = v > 0 ? __dadd_rn(v, -hb) : __dadd_rn(v, hb);
+            }
+        }
+        return v;
+    } else {
+        float f = __ldg(reinterpret_cast<const float*>(P.pos) + 3 * p + d);
+        if (P.fuse_center) {
+            f = __double2float_rn(__dadd_rn((double)f, -P.shift[d]));
+            if (P.periodic) {
+                double hb = P.boxsize / 2;
+                if (fabs((double)f) > hb)
+                    f = f > 0 ? __double2float_rn(__dadd_rn((double)f, -hb)) : __double2float_rn(__dadd_rn((double)f, hb));
+            }
+        }
+        return (double)f;
+    }
+}
+
+// inclusive box filter on the recentred centre (filter_shift.jl:50-58); centre of the recentred box is 0
+__device__ __forceinline__ bool in_image(const s2g_particles& P, double x, double y, double z)
+{
+    // corner = 0 -/+ halfsize ; !(lo <= v <= hi) is also false for NaN -> rejected, like the reference
+    return (-P.halfsize[0] <= x && x <= P.halfsize[0]) && (-P.halfsize[1] <= y && y <= P.halfsize[1]) &&
+           (-P.halfsize[2] <= z && z <= P.halfsize[2]);
+}
+
+// SPHKernels.jl shape functions w(u) for 0 <= u <= 1 (the norm*h_inv^dim prefactor cancels in every deposit:
+// kernel_norm*weight_per_pix = area/Σ(wk·dA)), evaluated in FP64.
+template <int KID>
+__device__ __forceinline__ double kernel_shape(double u)
+{
+    if (!(u < 1.0)) return 0.0;
+    const double t = 1.0 - u;
+    if (KID == S2G_KERNEL_CUBIC) {
+        if (u < 0.5) return fma(6.0 * (u - 1.0), u * u, 1.0);
+        return 2.0 * (t * t * t);
+    } else if (KID == S2G_KERNEL_QUINTIC) {
+        double b = fmax(2.0 / 3.0 - u, 0.0), c = fmax(1.0 / 3.0 - u, 0.0);
+        double a2 = t * t, b2 = b * b, c2 = c * c;
+        return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a2 * a2 * t));
+    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
+        double t2 = t * t;
+        return (t2 * t2) * fma(4.0, u, 1.0);
+    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
+        double t2 = t * t;
+        return (t2 * t2 * t2) * fma(fma(35.0 / 3.0, u, 6.0), u, 1.0);
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4) * fma(fma(fma(32.0, u, 25.0), u, 8.0), u, 1.0);
+    } else {  // WENDLAND_C8
+        double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4 * t2) * fma(fma(fma(fma(429.0, u, 450.0), u, 210.0), u, 50.0), u, 5.0);
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fire-and-forget FP64 add: compiles to RED.E.ADD.F64 (no return value -> no round trip)
+__device__ __forceinline__ void red_add(double* addr, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// internal launchers (defined in the per-path .cu files)
+// ------------------------------------------------------------------------------------------------
+int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image_dev);
+int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image_dev);
+int s2g_launch_footprints(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int dims, long long* bounds_dev);
+int s2g_launch_reduce_2d(s2g_ctx* ctx, const double* image_dev, long long nx, long long ny, int n_images,
+                         int reduce_image, double* out_dev);
+int s2g_launch_reduce_3d(s2g_ctx* ctx, const double* image_dev, long long npix, int reduce_image, double* out_dev);
+int s2g_launch_center_filter(s2g_ctx* ctx, const s2g_particles& P, void* pos_out_dev, uint8_t* mask_dev);
+int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
+                       double* map_dev, double* wmap_dev);
+int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, long long nside, long long* out_dev,
+                              long long cap, long long* count_dev);
+int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const void* q, long long n, int in_dtype,
+                       double len2pix, long long npix, int periodic, double* image_dev);
+int s2g_launch_accumulate_finite(s2g_ctx* ctx, double* sum_dev, const double* local_dev, long long n);
+int s2g_launch_synth(s2g_ctx* ctx, uint64_t seed, long long first_id, long long n, long long n_total, double box,
+                     double n_ngb, double sigma, int out_dtype, void* pos, void* hsml, void* m, void* rho, void* temp);
+int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double* rate_out);

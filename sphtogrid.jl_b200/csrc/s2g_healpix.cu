@@ -1,0 +1,424 @@
+// s2g_healpix.cu — HEALPix all-sky deposit (RING scheme), warp per particle.
+//
+// Replaces the particle loop of healpix_map (src/healpix_interpolation/main.jl:143-213):
+//   contributing_pixels (constributing_pixels.jl:7-22) -> Healpix.jl vec2ang / queryDiscRing / ang2pix
+//   calculate_weights   (pixel_weights.jl:87-140), weight_per_index (:34-76), contributing_area (:6-8),
+//   distance_to_pixel_center (:16-22) -> Healpix.jl pix2vecRing
+//   update_image!       (main.jl:25-45), particle_area_and_depth (main.jl:56-63)
+// The RING arithmetic is the published HEALPix algorithm (ring_above / ring2z / get_ring_info / pix2ang_ring /
+// ang2pix_ring / query_disc) that Healpix.jl ports; pixel numbers are 0-based (= Julia index - 1).
+//
+// Instead of materialising a pixel list per particle (the reference heap-allocates a Vector per particle) the
+// warp walks the disc ring by ring: each ring contributes one contiguous (mod ring length) run of pixels, lanes
+// stride over the run.  The pixel containing the particle centre is added when the disc walk did not visit it.
+#include "s2g_common.cuh"
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+
+struct HpGeom {
+    long long nside, npix, ncap, nl2, nl4;
+    double fact1_r2z, fact2_r2z;  // ring2z:   fact2 = 4/npix, fact1 = 2*nside*fact2
+    double fact1_p2a, fact2_p2a;  // pix2ang:  fact1 = 1.5*nside, fact2 = 3*nside^2
+    double ang_pix;               // sqrt(4π/npix)  (main.jl:144)
+};
+
+__host__ __device__ inline HpGeom make_hp(long long nside)
+{
+    HpGeom g;
+    g.nside = nside;
+    g.npix = 12 * nside * nside;
+    g.ncap = 2 * nside * (nside - 1);
+    g.nl2 = 2 * nside;
+    g.nl4 = 4 * nside;
+    g.fact2_r2z = 4.0 / (double)g.npix;
+    g.fact1_r2z = (double)(2 * nside) * g.fact2_r2z;
+    g.fact1_p2a = 1.5 * (double)nside;
+    g.fact2_p2a = 3.0 * (double)nside * (double)nside;
+    g.ang_pix = sqrt(4.0 * kPi / (double)g.npix);
+    return g;
+}
+
+__device__ __forceinline__ void hp_ring_info(const HpGeom& g, long long ring, long long& startpix, long long& ringpix,
+                                             bool& shifted)
+{
+    if (ring < g.nside) {
+        ringpix = 4 * ring; startpix = 2 * ring * (ring - 1); shifted = true;
+    } else if (ring <= 3 * g.nside) {
+        ringpix = g.nl4; startpix = g.ncap + (ring - g.nside) * g.nl4; shifted = (((ring - g.nside) & 1) == 0);
+    } else {
+        const long long nr = g.nl4 - ring;
+        ringpix = 4 * nr; startpix = g.npix - 2 * nr * (nr + 1); shifted = true;
+    }
+}
+
+__device__ __forceinline__ long long hp_ring_above(const HpGeom& g, double z)
+{
+    const double az = fabs(z);
+    if (az <= 2.0 / 3.0) return (long long)__dmul_rn((double)g.nside, __dadd_rn(2.0, -__dmul_rn(1.5, z)));
+    const long long iring = (long long)__dmul_rn((double)g.nside, __dsqrt_rn(__dmul_rn(3.0, __dadd_rn(1.0, -az))));
+    return (z > 0) ? iring : g.nl4 - iring - 1;
+}
+
+__device__ __forceinline__ double hp_ring2z(const HpGeom& g, long long ring)
+{
+    if (ring < g.nside) return __dadd_rn(1.0, -__dmul_rn((double)(ring * ring), g.fact2_r2z));
+    if (ring <= 3 * g.nside) return __dmul_rn((double)(g.nl2 - ring), g.fact1_r2z);
+    ring = g.nl4 - ring;
+    return __dadd_rn(__dmul_rn((double)(ring * ring), g.fact2_r2z), -1.0);
+}
+
+__device__ __forceinline__ long long hp_ang2pix_ring(const HpGeom& g, double theta, double phi)
+{
+    const double z = cos(theta), za = fabs(z);
+    double tt = fmod(phi, kTwoPi);
+    if (tt < 0) tt = __dadd_rn(tt, kTwoPi);
+    tt = __ddiv_rn(tt, 0.5 * kPi);
+    if (za <= 2.0 / 3.0) {
+        const double temp1 = __dmul_rn((double)g.nside, __dadd_rn(0.5, tt));
+        const double temp2 = __dmul_rn(__dmul_rn((double)g.nside, z), 0.75);
+        const long long jp = (long long)floor(__dadd_rn(temp1, -temp2));
+        const long long jm = (long long)floor(__dadd_rn(temp1, temp2));
+        const long long ir = g.nside + 1 + jp - jm;
+        const long long kshift = 1 - (ir & 1);
+        long long ip = (jp + jm - g.nside + kshift + 1) / 2;
+        ip = ((ip % g.nl4) + g.nl4) % g.nl4;
+        return g.ncap + (ir - 1) * g.nl4 + ip;
+    }
+    const double tp = __dadd_rn(tt, -floor(tt));
+    const double tmp = __dmul_rn((double)g.nside, __dsqrt_rn(__dmul_rn(3.0, __dadd_rn(1.0, -za))));
+    const long long jp = (long long)floor(__dmul_rn(tp, tmp));
+    const long long jm = (long long)floor(__dmul_rn(__dadd_rn(1.0, -tp), tmp));
+    const long long ir = jp + jm + 1;
+    long long ip = (long long)floor(__dmul_rn(tt, (double)ir));
+    ip = ((ip % (4 * ir)) + 4 * ir) % (4 * ir);
+    if (z > 0) return 2 * ir * (ir - 1) + ip;
+    return g.npix - 2 * ir * (ir + 1) + ip;
+}
+
+// colatitude-dependent part of pix2ang_ring for a whole ring: theta = acos(z_ring), returns sin/cos(theta) and the
+// azimuth step so that phi(j) = (j + 1 - off) * kPi / den  for the 0-based in-ring index j
+struct RingTrig {
+    double st, ct, off, den;
+};
+__device__ __forceinline__ RingTrig hp_ring_trig(const HpGeom& g, long long ring)
+{
+    RingTrig t;
+    double theta;
+    if (ring < g.nside) {
+        theta = acos(__dadd_rn(1.0, -__ddiv_rn((double)(ring * ring), g.fact2_p2a)));
+        t.off = 0.5; t.den = __dmul_rn(2.0, (double)ring);
+    } else if (ring <= 3 * g.nside) {
+        theta = acos(__ddiv_rn((double)(g.nl2 - ring), g.fact1_p2a));
+        t.off = 0.5 * (double)(1 + ((ring + g.nside) & 1));
+        t.den = __dmul_rn(2.0, (double)g.nside);
+    } else {
+        const long long rs = g.nl4 - ring;
+        theta = acos(__dadd_rn(-1.0, __ddiv_rn((double)(rs * rs), g.fact2_p2a)));
+        t.off = 0.5; t.den = __dmul_rn(2.0, (double)rs);
+    }
+    t.st = sin(theta);
+    t.ct = cos(theta);
+    return t;
+}
+
+// per-particle disc description
+struct Disc {
+    double px, py, pz, Dx;        // position relative to the observer and its norm (shared.jl:1-10)
+    double proj_h, hinv;          // asin(h/Dx) and its inverse
+    double theta, phi;            // vec2ang
+    double z0, xa, cosr;          // query_disc constants
+    long long ring_first, ring_last;      // all rings walked (cap rings + disc rings)
+    long long irmin, irmax;               // disc rings (others are full cap rings)
+    long long cpix;                       // pixel containing the centre (ang2pix)
+    bool full_sky;
+};
+
+__device__ __forceinline__ void make_disc(const HpGeom& g, Disc& d)
+{
+    // vec2ang (Healpix.jl): theta = acos(z/norm), phi = atan(y,x) (+2π if negative)
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.px, d.px), __dmul_rn(d.py, d.py)), __dmul_rn(d.pz, d.pz)));
+    d.theta = acos(__ddiv_rn(d.pz, nrm));
+    double ph = atan2(d.py, d.px);
+    if (ph < 0) ph = __dadd_rn(ph, kTwoPi);
+    d.phi = ph;
+    d.cpix = hp_ang2pix_ring(g, d.theta, d.phi);
+    const double r = d.proj_h;
+    d.full_sky = (r >= kPi);
+    if (d.full_sky) {
+        d.ring_first = 1; d.ring_last = g.nl4 - 1; d.irmin = g.nl4; d.irmax = 0;
+        return;
+    }
+    d.cosr = cos(r);
+    d.z0 = cos(d.theta);
+    d.xa = __ddiv_rn(1.0, __dsqrt_rn(__dmul_rn(__dadd_rn(1.0, -d.z0), __dadd_rn(1.0, d.z0))));
+    const double rlat1 = __dadd_rn(d.theta, -r);
+    d.irmin = hp_ring_above(g, cos(rlat1)) + 1;
+    d.ring_first = d.irmin;
+    if ((rlat1 <= 0) && (d.irmin > 1)) d.ring_first = 1;  // north pole inside the disc: rings 1..irmin-1 entirely
+    const double rlat2 = __dadd_rn(d.theta, r);
+    d.irmax = hp_ring_above(g, cos(rlat2));
+    d.ring_last = d.irmax;
+    if ((rlat2 >= kPi) && (d.irmax + 1 < g.nl4)) d.ring_last = g.nl4 - 1;  // south pole inside the disc
+}
+
+// pixel run of one ring: start index (0-based in ring, may need mod) and count (0 = ring not touched)
+__device__ __forceinline__ void ring_run(const HpGeom& g, const Disc& d, long long ring, long long nr, bool shifted,
+                                         long long& j0, long long& cnt)
+{
+    if (d.full_sky || ring < d.irmin || ring > d.irmax) {  // cap ring: the whole ring
+        j0 = 0; cnt = nr;
+        return;
+    }
+    const double z = hp_ring2z(g, ring);
+    const double x = __dmul_rn(__dadd_rn(d.cosr, -__dmul_rn(z, d.z0)), d.xa);
+    const double ysq = __dadd_rn(__dadd_rn(1.0, -__dmul_rn(z, z)), -__dmul_rn(x, x));
+    const double dphi = (ysq <= 0) ? 0.0 : atan2(__dsqrt_rn(ysq), x);
+    if (!(dphi > 0)) { j0 = 0; cnt = 0; return; }
+    const double shift = shifted ? 0.5 : 0.0;
+    const double f = __ddiv_rn((double)nr, kTwoPi);
+    long long ip_lo = (long long)floor(__dadd_rn(__dmul_rn(f, __dadd_rn(d.phi, -dphi)), -shift)) + 1;
+    long long ip_hi = (long long)floor(__dadd_rn(__dmul_rn(f, __dadd_rn(d.phi, dphi)), -shift));
+    if (ip_hi >= nr) { ip_lo -= nr; ip_hi -= nr; }
+    long long c = ip_hi - ip_lo + 1;
+    if (c <= 0) { j0 = 0; cnt = 0; return; }
+    if (c > nr) c = nr;  // the reference de-duplicates with unique! (constributing_pixels.jl:19)
+    j0 = ip_lo < 0 ? ip_lo + nr : ip_lo;
+    cnt = c;
+}
+
+// weight_per_index (pixel_weights.jl:34-76) for the pixel at in-ring index j of a ring with trig constants rt
+template <int KID>
+__device__ __forceinline__ void pixel_weight(const HpGeom& g, const Disc& d, const RingTrig& rt, long long j, double& A,
+                                             double& wk, bool& inside)
+{
+    const double phi = __ddiv_rn(__dmul_rn(__dadd_rn((double)(j + 1), -rt.off), kPi), rt.den);
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    const double cx = __dmul_rn(rt.st, cp), cy = __dmul_rn(rt.st, sp), cz = rt.ct;
+    // distance_to_pixel_center (pixel_weights.jl:16-22): d accumulates from 0.0, one rounded product at a time
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d.px, cx), __dmul_rn(d.py, cy)), __dmul_rn(d.pz, cz));
+    const double t = __ddiv_rn(dot, d.Dx);
+    const double dx = acos(fmin(t, 1.0));
+    const double u = __dmul_rn(dx, d.hinv);
+    // contributing_area (pixel_weights.jl:6-8) then / (ang_pix*Dx)^2 (:53)
+    const double inner = fabs(__dadd_rn(d.proj_h, -__dadd_rn(dx, -__dmul_rn(0.5, g.ang_pix))));
+    const double aD = __dmul_rn(g.ang_pix, d.Dx);
+    A = __ddiv_rn(__ddiv_rn(fmax(0.0, fmin(g.ang_pix, inner)), g.ang_pix), __dmul_rn(aD, aD));
+    inside = (u <= 1.0);
+    wk = inside ? kernel_shape<KID>(u) : 0.0;
+}
+
+template <int KID>
+__global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int calc_mean, double* __restrict__ amap,
+                                                 double* __restrict__ wmap, unsigned long long* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long touched = 0, fallback = 0, mapped = 0;
+    for (;;) {
+        long long p = 0;
+        if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= P.n) break;
+        const double q = ld_in(P.binq, p, P.in_dtype);
+        if (!calc_mean && q == 0.0) continue;  // main.jl:160-165
+        Disc d;
+        d.px = ld_pos(P, p, 0); d.py = ld_pos(P, p, 1); d.pz = ld_pos(P, p, 2);
+        const double hs = ld_in(P.hsml, p, P.in_dtype);
+        // get_norm (shared.jl:1-10): Σ pos[dim]^2 from zero, then sqrt
+        d.Dx = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.px, d.px), __dmul_rn(d.py, d.py)), __dmul_rn(d.pz, d.pz)));
+        if (d.Dx < hs) continue;  // main.jl:172-174
+        d.proj_h = asin(__ddiv_rn(hs, d.Dx));
+        d.hinv = __ddiv_rn(1.0, d.proj_h);
+        make_disc(g, d);
+
+        // ---- pass A
+        double sw = 0.0, sa = 0.0;
+        long long n_in = 0, n_tot = 0;
+        bool found_c = false;
+        for (long long ring = d.ring_first; ring <= d.ring_last; ++ring) {
+            long long sp, nr, j0, cnt;
+            bool sh;
+            hp_ring_info(g, ring, sp, nr, sh);
+            ring_run(g, d, ring, nr, sh, j0, cnt);
+            if (cnt == 0) continue;
+            const RingTrig rt = hp_ring_trig(g, ring);
+            for (long long t = lane; t < cnt; t += 32) {
+                long long j = j0 + t;
+                if (j >= nr) j -= nr;
+                double A, wk;
+                bool inside;
+                pixel_weight<KID>(g, d, rt, j, A, wk, inside);
+                sa += A;
+                ++n_tot;
+                if (inside) { sw = fma(wk, A, sw); ++n_in; }
+                if (sp + j == d.cpix) found_c = true;
+            }
+        }
+        found_c = __any_sync(0xffffffffu, found_c);
+        // the centre pixel, when the disc walk did not visit it (push! + unique!)
+        long long c_ring = 0, c_j = 0;
+        RingTrig c_rt{};
+        double cA = 0.0, cwk = 0.0;
+        bool c_inside = false;
+        if (!found_c) {
+            // ring of cpix
+            long long ring;
+            if (d.cpix < g.ncap) {
+                ring = (long long)((1 + (long long)floor(sqrt((double)(1 + 2 * d.cpix)))) >> 1);
+                while (2 * ring * (ring - 1) > d.cpix) --ring;
+                while (2 * ring * (ring + 1) <= d.cpix) ++ring;
+            } else if (d.cpix < g.npix - g.ncap) {
+                ring = (d.cpix - g.ncap) / g.nl4 + g.nside;
+            } else {
+                const long long rem = g.npix - 1 - d.cpix;  // 0-based from the end
+                long long rs = (long long)((1 + (long long)floor(sqrt((double)(1 + 2 * rem)))) >> 1);
+                while (2 * rs * (rs - 1) > rem) --rs;
+                while (2 * rs * (rs + 1) <= rem) ++rs;
+                ring = g.nl4 - rs;
+            }
+            long long sp, nr;
+            bool sh;
+            hp_ring_info(g, ring, sp, nr, sh);
+            c_ring = ring; c_j = d.cpix - sp;
+            c_rt = hp_ring_trig(g, c_ring);
+            pixel_weight<KID>(g, d, c_rt, c_j, cA, cwk, c_inside);
+            if (lane == 0) {
+                sa += cA;
+                ++n_tot;
+                if (c_inside) { sw = fma(cwk, cA, sw); ++n_in; }
+            }
+        }
+        sw = warp_sum(sw);
+        sa = warp_sum(sa);
+        n_in = warp_sum_ll(n_in);
+        n_tot = warp_sum_ll(n_tot);
+
+        // ---- normalisation (pixel_weights.jl:119-137, main.jl:32-33, :188-193)
+        bool fb = false;
+        double n_distr, wpp;
+        if (sw == 0.0) {
+            fb = true;
+            n_distr = (double)n_tot;
+            wpp = (sa != 0.0) ? n_distr / sa : 1.0;
+            if (lane == 0) ++fallback;
+        } else {
+            n_distr = (double)n_in;
+            wpp = n_distr / sw;
+        }
+        double dz = __dmul_rn(2.0, hs);
+        const double area = __ddiv_rn(__ddiv_rn(ld_in(P.m, p, P.in_dtype), ld_in(P.rho, p, P.in_dtype)), dz);
+        const double aD = __dmul_rn(g.ang_pix, d.Dx);
+        dz = __ddiv_rn(dz, __dmul_rn(aD, aD));
+        const double kernel_norm = area / n_distr;
+        const double area_norm = kernel_norm * wpp * ld_in(P.w, p, P.in_dtype) * dz;
+        const bool q_finite = isfinite(q);
+
+        // ---- pass B
+        for (long long ring = d.ring_first; ring <= d.ring_last; ++ring) {
+            long long sp, nr, j0, cnt;
+            bool sh;
+            hp_ring_info(g, ring, sp, nr, sh);
+            ring_run(g, d, ring, nr, sh, j0, cnt);
+            if (cnt == 0) continue;
+            const RingTrig rt = hp_ring_trig(g, ring);
+            for (long long t = lane; t < cnt; t += 32) {
+                long long j = j0 + t;
+                if (j >= nr) j -= nr;
+                double A, wk;
+                bool inside;
+                pixel_weight<KID>(g, d, rt, j, A, wk, inside);
+                if (fb) wk = 1.0;
+                const double pw = area_norm * wk * A;
+                if (pw != 0.0 || !q_finite) {
+                    red_add(amap + sp + j, q * pw);
+                    red_add(wmap + sp + j, pw);
+                }
+                ++touched;
+            }
+        }
+        if (!found_c && lane == 0) {
+            const double pw = area_norm * (fb ? 1.0 : cwk) * cA;
+            if (pw != 0.0 || !q_finite) {
+                red_add(amap + d.cpix, q * pw);
+                red_add(wmap + d.cpix, pw);
+            }
+            ++touched;
+        }
+        if (lane == 0) ++mapped;
+    }
+    touched = (unsigned long long)warp_sum_ll((long long)touched);
+    if (lane == 0) {
+        if (touched) { atomicAdd(&counters[CNT_TOUCHED], touched); atomicAdd(&counters[CNT_FOOTPRINT], touched); }
+        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
+        if (mapped) { atomicAdd(&counters[CNT_MAPPED], mapped); atomicAdd(&counters[CNT_SCATTER], mapped); }
+    }
+}
+
+// single-thread pixel list in the reference's order (test hook for the bit-exact pixel-set contract)
+__global__ void k_healpix_pixels(double px, double py, double pz, double radius, HpGeom g, long long* out,
+                                 long long cap, long long* count)
+{
+    Disc d;
+    d.px = px; d.py = py; d.pz = pz;
+    d.Dx = 1.0;
+    d.proj_h = radius;
+    d.hinv = 1.0 / radius;
+    make_disc(g, d);
+    long long n = 0;
+    bool found = false;
+    for (long long ring = d.ring_first; ring <= d.ring_last; ++ring) {
+        long long sp, nr, j0, cnt;
+        bool sh;
+        hp_ring_info(g, ring, sp, nr, sh);
+        ring_run(g, d, ring, nr, sh, j0, cnt);
+        // reference order inside a ring: [0..ip_hi] first, then the wrapped part (query_disc appends that way)
+        if (cnt > 0 && j0 + cnt > nr) {
+            for (long long j = 0; j < j0 + cnt - nr; ++j) { if (n < cap) out[n] = sp + j; ++n; if (sp + j == d.cpix) found = true; }
+            for (long long j = j0; j < nr; ++j) { if (n < cap) out[n] = sp + j; ++n; if (sp + j == d.cpix) found = true; }
+        } else
+            for (long long t = 0; t < cnt; ++t) { if (n < cap) out[n] = sp + j0 + t; ++n; if (sp + j0 + t == d.cpix) found = true; }
+    }
+    if (!found) { if (n < cap) out[n] = d.cpix; ++n; }
+    *count = n;
+}
+
+template <int KID>
+int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, double* amap, double* wmap)
+{
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    const HpGeom g = make_hp(nside);
+    int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 8);
+    k_healpix<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, g, calc_mean, amap, wmap, ctx->d_counters);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}
+
+}  // namespace
+
+int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean, double* amap,
+                       double* wmap)
+{
+    if (P.n <= 0) return S2G_OK;
+    switch (kernel) {
+    case S2G_KERNEL_CUBIC: return launch_healpix_k<S2G_KERNEL_CUBIC>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_QUINTIC: return launch_healpix_k<S2G_KERNEL_QUINTIC>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C2: return launch_healpix_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C4: return launch_healpix_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C6: return launch_healpix_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C8: return launch_healpix_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, nside, calc_mean, amap, wmap);
+    }
+    s2g_set_error("unknown kernel id %d", kernel);
+    return S2G_EINVAL;
+}
+
+int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, long long nside, long long* out,
+                              long long cap, long long* count)
+{
+    const HpGeom g = make_hp(nside);
+    k_healpix_pixels<<<1, 1, 0, ctx->stream>>>(pos[0], pos[1], pos[2], radius, g, out, cap, count);
+    S2G_CUDA(cudaGetLastError());
+    return S2G_OK;
+}

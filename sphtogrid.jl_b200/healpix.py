@@ -1,0 +1,63 @@
+"""healpix_map — host mirror of src/healpix_interpolation/main.jl:92-227; the particle loop is
+libsphtogrid_cuda's s2g_healpix_deposit.  filter_sort_particles (filter_particles.jl:17-54) is O(N log N) host
+logic and is reproduced literally, including its quirks (in-place recentre, sorted[mask], BoundsError)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import F64, check, default_context, lib, ptr
+from .mapping import _as_pos, _kernel_id
+
+
+def find_in_shell(dx, radius_limits):
+    """filter_particles.jl:6-8"""
+    return (radius_limits[0] <= dx) & (dx <= radius_limits[1])
+
+
+def filter_sort_particles(Pos, Hsml, M, Rho, Bin_q, Weights, center, radius_limits, calc_mean):
+    """filter_particles.jl:17-54"""
+    pos = _as_pos(Pos)
+    pos -= np.asarray(center, dtype=pos.dtype)[None, :]                      # Pos .-= center (in place)
+    dx = np.sqrt(pos[:, 0] ** 2 + pos[:, 1] ** 2 + pos[:, 2] ** 2)
+    sel = find_in_shell(dx, radius_limits)
+    if not calc_mean:
+        sel = sel[np.asarray(Bin_q)[sel] > 0.0]
+    srt = np.argsort(dx, kind="stable")[::-1]                                # reverse(sortperm(Δx))
+    if sel.shape[0] != srt.shape[0]:
+        raise IndexError(f"BoundsError: attempt to access {srt.shape[0]}-element Vector{{Int64}} at index "
+                         f"[{sel.shape[0]}-element BitVector]")
+    idx = srt[sel]
+    g = lambda a: np.ascontiguousarray(np.asarray(a)[idx])
+    return np.ascontiguousarray(pos[idx]), g(Hsml), g(M), g(Rho), g(Bin_q), g(Weights)
+
+
+def healpix_deposit(pos, hsml, m, rho, bin_q, weights, Nside, kernel, calc_mean=True, ctx=None, return_stats=False):
+    """The particle loop of healpix_map (main.jl:143-213) on already filtered, observer-centred particles."""
+    ctx = ctx or default_context()
+    p = np.ascontiguousarray(_as_pos(pos), dtype=np.float64)
+    n = p.shape[0]
+    npix = 12 * int(Nside) ** 2
+    amap = np.zeros(npix); wmap = np.zeros(npix)
+    st = _lib.Stats()
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    check(lib().s2g_healpix_deposit(ctx.handle, ptr(p), ptr(f(hsml)), ptr(f(m)), ptr(f(rho)), ptr(f(bin_q)),
+                                    ptr(f(weights)), n, F64, int(Nside), _kernel_id(kernel), int(calc_mean),
+                                    ptr(amap), ptr(wmap), C.byref(st)))
+    return (amap, wmap, st.asdict()) if return_stats else (amap, wmap)
+
+
+def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), radius_limits=(0.0, np.inf),
+                Nside=1024, kernel, show_progress=True, output_from_all_workers=False, calc_mean=True, ctx=None):
+    """Calculate an allsky map from SPH particles.  Returns `(image, weight_image)` in RING order (0-based storage =
+    Julia pixels[i+1]); divide to reduce the image (main.jl:76-77)."""
+    npix = 12 * int(Nside) ** 2
+    if (not calc_mean) and np.sum(Bin_q) == 0:
+        return np.zeros(npix), np.zeros(npix)
+    if _as_pos(Pos).dtype != np.float64:
+        raise TypeError("healpix_map requires Float64 inputs (method signatures `where T`, pixel_weights.jl:87-91)")
+    pos, hsml, m, rho, bq, w = filter_sort_particles(Pos, Hsml, M, Rho, Bin_q, Weights, center, radius_limits,
+                                                     calc_mean)
+    return healpix_deposit(pos, hsml, m, rho, bq, w, Nside, kernel, calc_mean, ctx=ctx)

@@ -1,0 +1,147 @@
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from util import KERNELS, assert_parity, kern, random_particles
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kernel", ["Cubic", "WendlandC6", "Quintic"])
+def test_deposit_3d_parity(s2g, oracle, kernel):
+    pos, hsml, m, rho, q, w = random_particles(41, 3000, box=11.0, hmax=1.0)
+    hsml[:200] *= 0.02
+    q[3:30] = 0.0
+    npix = 48
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=npix)
+    for calc_mean in (False, True):
+        got, st = s2g.cic_mapping_3D(pos, hsml, m, rho, q, w, param=par, kernel=kern(s2g, kernel, 3),
+                                     calc_mean=calc_mean, return_stats=True)
+        ref, ost = oracle.cic_mapping_3d(pos, hsml, m, rho, q, w, par.len2pix, npix, kernel, 3, calc_mean)
+        assert_parity(got, ref, what=f"3D {kernel} calc_mean={calc_mean}")
+        for k in ("n_mapped", "footprint_pixels", "n_fallback", "touched_pixels"):
+            assert st[k] == ost[k], k
+
+
+def test_sphmapping_3d_end_to_end(s2g, oracle):
+    pos, hsml, m, rho, q, w = random_particles(43, 4000, box=7.0, hmax=0.5, dtype=np.float32, center=3.0)
+    kw = dict(center=[3.0, 3.0, 3.0], x_size=6.0, y_size=6.0, z_size=6.0, Npixels=40, boxsize=6.0)
+    for red in (True, False):
+        p1, p2 = pos.copy(), pos.copy()
+        got = s2g.sphMapping(p1, hsml, m, rho, q, w, param=s2g.mappingParameters(**kw), kernel=s2g.WendlandC6(3),
+                             dimensions=3, reduce_image=red, show_progress=False)
+        ref = oracle.sph_mapping(p2, hsml, m, rho, q, w, param=oracle.mapping_parameters(**kw), kernel="WendlandC6",
+                                 dimensions=3, reduce_image=red)
+        assert np.array_equal(p1, p2)
+        assert got.shape == (40, 40, 40)
+        assert_parity(got, ref, what=f"sphMapping 3D reduce={red}")
+
+
+# ---------------------------------------------------------------- HEALPix
+def _gpu_pixels(s2g, pos, radius, nside, cap=1 << 16):
+    from sphtogrid_b200 import _lib
+    out = np.zeros(cap, dtype=np.int64)
+    cnt = C.c_int64(0)
+    p = (C.c_double * 3)(*pos)
+    _lib.check(s2g.lib().s2g_healpix_pixels(s2g.default_context().handle, p, float(radius), nside, _lib.ptr(out), cap,
+                                            C.byref(cnt)))
+    assert cnt.value <= cap
+    return out[:cnt.value]
+
+
+@pytest.mark.parametrize("nside", [1, 4, 64, 512, 2048])
+def test_healpix_pixel_lists_identical(s2g, oracle, nside):
+    """pixel-index work is bit-exact: same pixel SET per particle as the oracle's contributing_pixels"""
+    rng = np.random.default_rng(nside)
+    L = oracle.lib()
+    buf = np.zeros(1 << 16, dtype=np.int64)
+    ang = math.sqrt(4 * math.pi / (12 * nside * nside))
+    cases = []
+    for _ in range(150):
+        v = rng.normal(size=3)
+        cases.append((v, min(3.0, ang * rng.uniform(0.05, 40.0))))
+    cases += [(np.array([0.0, 0.0, 1.0]), 5 * ang), (np.array([0.0, 0.0, -1.0]), 5 * ang),
+              (np.array([1e-9, 0.0, 1.0]), 3 * ang), (np.array([1.0, -1e-12, 0.0]), 4 * ang),
+              (np.array([1.0, 0.0, 0.0]), 4 * ang), (np.array([-1.0, 1e-13, 0.3]), 10 * ang)]
+    for v, r in cases:
+        if (math.pi * r * r) / (ang * ang) > 50000:
+            r = ang * 100
+        n = L.s2go_hp_contributing_pixels(nside, v.ctypes.data_as(C.POINTER(C.c_double)), r,
+                                          buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size)
+        assert n >= 0
+        ref = buf[:n]
+        got = _gpu_pixels(s2g, v, r, nside)
+        assert np.array_equal(np.sort(got), np.sort(ref)), (nside, v, r)
+
+
+@pytest.mark.parametrize("kernel", ["WendlandC4", "Cubic"])
+@pytest.mark.parametrize("nside", [32, 256])
+def test_healpix_deposit_parity(s2g, oracle, kernel, nside):
+    rng = np.random.default_rng(5)
+    n = 1500
+    pos = rng.normal(size=(n, 3)) * 60.0
+    hsml = rng.random(n) * 6.0 + 0.2
+    hsml[:100] *= 0.01                       # sub-pixel discs -> only the centre pixel -> fallback branch
+    pos[100:110] *= 0.01                     # closer than hsml -> skipped
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 1e4; w = rng.random(n) + 0.5
+    q[200:220] = 0.0
+    for calc_mean in (True, False):
+        a, wm, st = s2g.healpix_deposit(pos, hsml, m, rho, q, w, nside, kern(s2g, kernel), calc_mean,
+                                        return_stats=True)
+        ra, rw, ost = oracle.healpix_deposit(pos, hsml, m, rho, q, w, nside, kernel, 2, calc_mean)
+        assert st["n_mapped"] == ost["n_mapped"] and st["n_fallback"] == ost["n_fallback"]
+        assert st["touched_pixels"] == ost["touched_pixels"]
+        # acos(dot/r) at sub-pixel angles amplifies a last-ulp difference of sin/cos/acos between CUDA's and glibc's
+        # libm by ~eps/proj_hsml^2 (DESIGN.md §HEALPix conditioning); 1e-10 is demanded where the discs are resolved
+        tol = 1e-10 if nside <= 64 else 2e-9
+        assert_parity(wm, rw, rtol=tol, what=f"healpix weight map nside={nside}")
+        assert_parity(a, ra, rtol=tol, what=f"healpix map nside={nside}")
+        assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12)
+
+
+def test_healpix_map_api(s2g, oracle):
+    """src/precompile.jl:9-23 fixture (7 cluster positions, Nside 128) through healpix_map, incl. Q1"""
+    center = np.array([247.980, 245.480, 255.290]) * 1.0e3
+    hp_pos = np.array([[225160.875, 256677.5625, 242031.765625], [245040.453125, 327781.84375, 246168.6875],
+                       [252454.0, 238890.296875, 233772.890625], [202408.359375, 245067.234375, 249614.09375],
+                       [176696.22, 266631.8, 315976.38], [307184.78125, 247627.078125, 230736.484375],
+                       [244450.578125, 255851.78125, 253668.1875]])
+    hp_hsml = np.array([1771.7005615234375, 2177.5625, 714.1318359375, 798.90478515625, 1067.0657,
+                        1813.0419921875, 1711.311767578125])
+    one = np.ones(7)
+    p1, p2 = hp_pos.copy(), hp_pos.copy()
+    a, wm = s2g.healpix_map(p1, hp_hsml, one, one, one, one, center=center, kernel=s2g.WendlandC4(2), Nside=128,
+                            show_progress=False)
+    ra, rw = oracle.healpix_map(p2, hp_hsml, one, one, one, one, center=center, kernel="WendlandC4", nside=128)
+    assert np.array_equal(p1, p2)
+    assert_parity(a, ra, what="precompile fixture map")
+    assert_parity(wm, rw, what="precompile fixture weights")
+    with pytest.raises(IndexError):
+        s2g.healpix_map(hp_pos.copy(), hp_hsml, one, one, np.array([1, 1, 0, 1, 1, 1, 1.0]), one, center=center,
+                        kernel=s2g.WendlandC4(2), Nside=128, calc_mean=False)
+
+
+# ---------------------------------------------------------------- CIC / TSC stencils
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_stencils_parity(s2g, oracle, order, dims, periodic):
+    pos, hsml, m, rho, q, w = random_particles(51, 20000, box=10.4)
+    npix = 64 if dims == 2 else 32
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=npix)
+    fn = s2g.cic_deposit if order == 2 else s2g.tsc_deposit
+    got = fn(pos, q, param=par, dimensions=dims, average=False, periodic=periodic)
+    ref = oracle.stencil_deposit(order, dims, pos, q, par.len2pix, npix, periodic)
+    assert_parity(got, ref, rtol=1e-12, what=f"stencil order={order} dims={dims}")
+    if not periodic:
+        inside = np.all(np.abs(pos[:, :dims]) < 5.0 - 1.5 * par.pixelSideLength, axis=1)
+        if dims == 3:
+            assert got[:, 1].sum() <= pos.shape[0] + 1e-9
+        assert got[:, 1].sum() >= inside.sum() - 1e-6
+    else:
+        if dims == 3:
+            assert math.isclose(got[:, 1].sum(), pos.shape[0], rel_tol=1e-12)
+    avg = fn(pos, q, param=par, dimensions=dims, average=True, periodic=periodic)
+    assert_parity(avg.ravel(), oracle.stencil_average(ref), rtol=1e-12, what="average")

@@ -1,0 +1,162 @@
+"""CPU-only tests: host mirror of the reference interface, the C-ABI library's export table, and the N>1 host logic
+(world_size-2 gloo).  No compute call into the CUDA library happens here."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(s2g):
+    hdr = open(os.path.join(ROOT, "include", "sphtogrid_cuda.h")).read()
+    declared = set(re.findall(r"S2G_API\s+[\w\s\*]+?\b(s2g_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = s2g.lib()
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/sphtogrid_cuda.h but not exported"
+    assert declared == set(s2g.EXPORTED_SYMBOLS), declared ^ set(s2g.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in L.s2g_version()
+
+
+def test_no_cpu_fallback(s2g):
+    if s2g.lib().s2g_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(s2g.S2GError, match="no CUDA device"):
+        s2g.Context(0)
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=8)
+    one = np.ones(4)
+    with pytest.raises(s2g.S2GError):
+        s2g.sphMapping(np.zeros((4, 3)), one, one, one, one, param=par, kernel=s2g.Cubic(), show_progress=False)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sphtogrid.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), \
+                    f"{f} mentions the oracle: the product path must never route through it"
+
+
+# ---- test/runtests.jl:38-58 through the product's mappingParameters
+def test_mapping_parameters_reference_cases(s2g):
+    with pytest.raises(ValueError, match="Giving a center position requires extent in x, y and z direction."):
+        s2g.mappingParameters()
+    with pytest.raises(ValueError, match="Please specify pixelSideLength or number of pixels!"):
+        s2g.mappingParameters(center=[0.0, 0.0, 0.0], x_lim=[-1.0, 1.0], y_lim=[-1.0, 1.0], z_lim=[-1.0, 1.0])
+    s2g.mappingParameters(center=[0.0, 0.0, 0.0], x_lim=[-1.0, 1.0], y_lim=[-1.0, 1.0], z_lim=[-1.0, 1.0], Npixels=100)
+    p = s2g.mappingParameters(center=[0.0, 0.0, 0.0], x_lim=[-1.0, 1.0], y_lim=[-1.0, 1.0], z_lim=[-1.0, 1.0],
+                              pixelSideLength=0.2)
+    assert p.Npixels.tolist() == [10, 10, 10]
+
+
+def test_mapping_parameters_match_oracle_bitwise(s2g, oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        c = rng.normal(size=3) * 100
+        sz = rng.random(3) * 50 + 0.1
+        n = int(rng.integers(1, 5000))
+        box = float(rng.choice([-1.0, 100.0]))
+        if rng.random() < 0.5:
+            kw = dict(center=c.tolist(), x_size=sz[0], y_size=sz[1], z_size=sz[2], Npixels=n, boxsize=box)
+        else:
+            kw = dict(x_lim=[c[0] - sz[0], c[0] + sz[0]], y_lim=[c[1] - sz[1], c[1] + sz[1]],
+                      z_lim=[c[2] - sz[2], c[2] + sz[2]], pixelSideLength=float(sz.max() / n), boxsize=box)
+        a = s2g.mappingParameters(**kw)
+        b = oracle.mapping_parameters(**kw)
+        for f in ("x_lim", "y_lim", "z_lim", "center", "halfsize", "Npixels"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        assert a.len2pix == b.len2pix and a.pixelSideLength == b.pixelSideLength and a.periodic == b.periodic
+        a2 = s2g.recentred_parameters(a)
+        _, b2 = oracle.center_particles(np.zeros((1, 3)), b)
+        assert a2.len2pix == b2.len2pix and np.array_equal(a2.halfsize, b2.halfsize)
+        assert a2.center.tolist() == [0.0, 0.0, 0.0]
+
+
+# ---- test/runtests.jl:488-506
+def test_weight_functions(s2g):
+    assert s2g.part_weight_one(1)[0] == 1.0
+    par = s2g.mappingParameters(center=[3.0, 3.0, 3.0], x_size=6.0, y_size=6.0, z_size=6.0, Npixels=200, boxsize=6.0)
+    assert np.isclose(s2g.part_weight_physical(1, par)[0], par.pixelSideLength * 3.085678e21)
+    assert np.isclose(s2g.part_weight_physical(1)[0], 3.085678e21)
+    assert np.isclose(s2g.part_weight_emission([0.5, 0.5], [0.5, 0.5])[0], 0.1767766952966369)
+    assert np.isclose(s2g.part_weight_spectroscopic([0.5, 0.5], [0.5, 0.5])[0], 0.4204482076268573)
+
+
+def test_kernel_types(s2g):
+    assert s2g.Cubic().dim == 3 and s2g.WendlandC6(2).dim == 2 and s2g.WendlandC4(float, 2).dim == 2
+    ids = [k().kernel_id for k in (s2g.Cubic, s2g.Quintic, s2g.WendlandC2, s2g.WendlandC4, s2g.WendlandC6,
+                                   s2g.WendlandC8)]
+    assert ids == [0, 1, 2, 3, 4, 5]
+    with pytest.raises(ValueError):
+        s2g.Cubic(4)
+
+
+def test_domain_decomposition_matches_reference(s2g, oracle):
+    for n, w in [(10, 3), (7, 7), (5, 8), (1000003, 8), (0, 2)]:
+        assert s2g.domain_decomposition(n, w) == oracle.domain_decomposition(n, w)
+
+
+def test_filter_sort_particles_host_logic(s2g, oracle):
+    rng = np.random.default_rng(2)
+    n = 200
+    pos = rng.normal(size=(n, 3)) * 30
+    args = [rng.random(n) for _ in range(5)]
+    c = [1.0, 2.0, 3.0]
+    a = s2g.filter_sort_particles(pos.copy(), *args, c, [5.0, 60.0], True)
+    b = oracle.filter_sort_particles(pos.copy(), *args, c, [5.0, 60.0], True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+# ---- N>1 host logic over gloo, world_size 2 (the deposit itself is stood in for by the oracle: CPU box)
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from oracle import oracle as orc
+    s2g = ge.load_package()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(77)
+    n = 1001
+    pos = (rng.random((n, 3)) - 0.5) * 10; hs = rng.random(n) * 0.8 + 0.01
+    m = rng.random(n) + 0.1; rho = rng.random(n) + 0.1; qq = rng.random(n); w = rng.random(n) + 0.5
+    s, e = s2g.distributed.shard_range(n, world, rank)
+    part, _ = orc.cic_mapping_2d(pos[s:e], hs[s:e], m[s:e], rho[s:e], qq[s:e], w[s:e], 6.4, 64, "WendlandC6", 2, True)
+    if rank == 1:
+        part[5, 0] = np.nan  # a poisoned partial map entry is skipped by the reference's accumulate (cic.jl:63-69)
+    total = s2g.distributed.combine_partial_images(part, finite_guard=True)
+    if rank == 0:
+        q.put((s, e, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_shard_and_reduce(s2g, oracle):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    s, e, total = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(77)
+    n = 1001
+    pos = (rng.random((n, 3)) - 0.5) * 10; hs = rng.random(n) * 0.8 + 0.01
+    m = rng.random(n) + 0.1; rho = rng.random(n) + 0.1; qq = rng.random(n); w = rng.random(n) + 0.5
+    assert (s, e) == (0, 500)
+    a, _ = oracle.cic_mapping_2d(pos[:500], hs[:500], m[:500], rho[:500], qq[:500], w[:500], 6.4, 64, "WendlandC6", 2,
+                                 True)
+    b, _ = oracle.cic_mapping_2d(pos[500:], hs[500:], m[500:], rho[500:], qq[500:], w[500:], 6.4, 64, "WendlandC6", 2,
+                                 True)
+    b[5, 0] = 0.0
+    assert np.array_equal(total, a + b)
