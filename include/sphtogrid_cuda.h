@@ -83,7 +83,12 @@ typedef struct {
     int64_t n_pairs;          /* (particle,tile) pairs of the gather path              */
     int64_t n_scatter;        /* particles deposited by the scatter kernel             */
     int64_t n_gather;         /* particles deposited by the gather kernel              */
-    double ms_h2d, ms_prep, ms_sort, ms_norm, ms_deposit, ms_epilogue, ms_d2h, ms_total;
+    int64_t n_launches;       /* kernels launched by the library for this call          */
+    /* device times [ms] from CUDA events on the context stream:
+     * h2d / compute / d2h / total bracket the host entry points; prep (classify, scans, lists), sort (pair
+     * expansion + radix sort + tile ranges), norm (pass A kernel), deposit (scatter + gather kernels),
+     * epilogue (reduce_image) are per-phase sums inside `compute`. */
+    double ms_h2d, ms_compute, ms_d2h, ms_total, ms_prep, ms_sort, ms_norm, ms_deposit, ms_epilogue;
 } s2g_stats;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -96,6 +101,11 @@ S2G_API const char* s2g_version(void);
 /* use an externally owned stream (e.g. torch's current stream, passed as cudaStream_t) */
 S2G_API int s2g_set_stream(s2g_ctx* ctx, void* cuda_stream);
 S2G_API int s2g_set_strategy(s2g_ctx* ctx, int strategy /* s2g_strategy */);
+/* Pass A of the 2D deposit (calculate_weights, cic_2D.jl:11-72) sums w(u)*dA over the footprint.  For footprints
+ * that are not clipped by the image and resolved by >= 32..96 pixels per kernel radius (kernel dependent) that sum
+ * equals h^2 * ∫w(u) 2πu du to better than 2e-13 relative (tools/analytic_norm_study.py) and the closed form is
+ * used by default.  on != 0 forces the numerical sum for every particle. */
+S2G_API int s2g_set_exact_norm(s2g_ctx* ctx, int on);
 S2G_API int s2g_get_stats(s2g_ctx* ctx, s2g_stats* out);
 /* pinned host buffers for the end-to-end path */
 S2G_API int s2g_host_alloc(void** out, uint64_t bytes);

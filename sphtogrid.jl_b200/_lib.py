@@ -28,9 +28,9 @@ class S2GError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_in", "n_mapped", "footprint_pixels", "touched_pixels", "n_fallback",
-                                         "n_pairs", "n_scatter", "n_gather")] + \
-               [(n, C.c_double) for n in ("ms_h2d", "ms_prep", "ms_sort", "ms_norm", "ms_deposit", "ms_epilogue",
-                                          "ms_d2h", "ms_total")]
+                                         "n_pairs", "n_scatter", "n_gather", "n_launches")] + \
+               [(n, C.c_double) for n in ("ms_h2d", "ms_compute", "ms_d2h", "ms_total", "ms_prep", "ms_sort",
+                                          "ms_norm", "ms_deposit", "ms_epilogue")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -61,6 +61,7 @@ _SIGS = {
     "s2g_version": (C.c_char_p, []),
     "s2g_set_stream": (C.c_int, [_vp, _vp]),
     "s2g_set_strategy": (C.c_int, [_vp, C.c_int]),
+    "s2g_set_exact_norm": (C.c_int, [_vp, C.c_int]),
     "s2g_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "s2g_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "s2g_host_free": (C.c_int, [_vp]),
@@ -134,12 +135,14 @@ def dbl3(v):
 class Context:
     """One CUDA device + stream + scratch arena (s2g_ctx)."""
 
-    def __init__(self, device: int = 0, strategy: str = "auto"):
+    def __init__(self, device: int = 0, strategy: str = "auto", exact_norm: bool = False):
         self._h = _vp()
         check(lib().s2g_init(int(device), C.byref(self._h)))
         self.device = device
         if strategy != "auto":
             self.set_strategy(strategy)
+        if exact_norm:
+            self.set_exact_norm(True)
 
     @property
     def handle(self):
@@ -149,6 +152,9 @@ class Context:
 
     def set_strategy(self, strategy: str):
         check(lib().s2g_set_strategy(self.handle, STRATEGY[strategy]))
+
+    def set_exact_norm(self, on: bool):
+        check(lib().s2g_set_exact_norm(self.handle, int(bool(on))))
 
     def set_stream(self, cuda_stream: int):
         check(lib().s2g_set_stream(self.handle, _vp(int(cuda_stream))))

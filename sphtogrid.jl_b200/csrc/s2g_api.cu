@@ -73,6 +73,7 @@ extern "C" int s2g_shutdown(s2g_ctx* ctx)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& t : ctx->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -108,6 +109,36 @@ extern "C" int s2g_set_strategy(s2g_ctx* ctx, int strategy)
               "s2g_set_strategy: unknown strategy %d", strategy);
     ctx->strategy = strategy;
     return S2G_OK;
+}
+
+extern "C" int s2g_set_exact_norm(s2g_ctx* ctx, int on)
+{
+    S2G_CHECK(ctx != nullptr, S2G_EINVAL, "s2g_set_exact_norm: ctx is NULL");
+    ctx->exact_norm = on ? 1 : 0;
+    return S2G_OK;
+}
+
+int s2g_phase_begin(s2g_ctx* ctx, int phase)
+{
+    if (ctx->timers_used == ctx->timers.size()) {
+        s2g_ctx::timer t;
+        t.phase = phase;
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        ctx->timers.push_back(t);
+    }
+    const int h = (int)ctx->timers_used++;
+    ctx->timers[h].phase = phase;
+    cudaEventRecord(ctx->timers[h].a, ctx->stream);
+    return h;
+}
+
+void s2g_phase_end(s2g_ctx* ctx, int handle)
+{
+    if (handle < 0) return;
+    cudaEventRecord(ctx->timers[handle].b, ctx->stream);
 }
 
 int s2g_scratch(s2g_ctx* ctx, const char* name, size_t bytes, void** out)
@@ -192,6 +223,8 @@ static int stats_begin(s2g_ctx* ctx, long long n_in)
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->stats.n_in = n_in;
     ctx->host_pairs = 0;
+    ctx->timers_used = 0;
+    ctx->launches = 0;
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
     return S2G_OK;
 }
@@ -209,6 +242,20 @@ static int stats_collect(s2g_ctx* ctx)
     ctx->stats.n_pairs = (int64_t)ctx->host_pairs;
     ctx->stats.n_scatter = (int64_t)ctx->h_counters[CNT_SCATTER];
     ctx->stats.n_gather = (int64_t)ctx->h_counters[CNT_GATHER];
+    double ph[PH_N] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < ctx->timers_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->timers[i].a, ctx->timers[i].b) == cudaSuccess)
+            ph[ctx->timers[i].phase] += ms;
+        else
+            cudaGetLastError();
+    }
+    ctx->stats.ms_prep = ph[PH_PREP];
+    ctx->stats.ms_sort = ph[PH_SORT];
+    ctx->stats.ms_norm = ph[PH_NORM];
+    if (ph[PH_DEPOSIT] > 0) ctx->stats.ms_deposit = ph[PH_DEPOSIT];
+    if (ph[PH_EPILOGUE] > 0) ctx->stats.ms_epilogue = ph[PH_EPILOGUE];
+    ctx->stats.n_launches = ctx->launches;
     return S2G_OK;
 }
 
@@ -369,7 +416,7 @@ extern "C" int s2g_deposit_2d(s2g_ctx* ctx, const void* pos, const void* hsml, c
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_deposit = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
     if (stats) *stats = ctx->stats;
@@ -417,7 +464,7 @@ extern "C" int s2g_deposit_3d(s2g_ctx* ctx, const void* pos, const void* hsml, c
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_deposit = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
     if (stats) *stats = ctx->stats;
@@ -614,7 +661,7 @@ extern "C" int s2g_sphmap(s2g_ctx* ctx, int32_t dims, const void* pos, const voi
     S2G_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_deposit = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_epilogue = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[3], ctx->ev[4]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[4]);
@@ -673,7 +720,7 @@ extern "C" int s2g_healpix_deposit(s2g_ctx* ctx, const void* pos, const void* hs
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_deposit = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
     if (stats) *stats = ctx->stats;
@@ -757,7 +804,7 @@ extern "C" int s2g_stencil_deposit(s2g_ctx* ctx, int32_t order, int32_t dims, co
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    ctx->stats.ms_deposit = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
     if (stats) *stats = ctx->stats;

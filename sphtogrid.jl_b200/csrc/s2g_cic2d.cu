@@ -160,6 +160,7 @@ static int launch_scatter2d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
     blocks = min(blocks, ctx->sm_count * 8);
     k_scatter2d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }
 
@@ -260,8 +261,11 @@ int s2g_launch_reduce_2d(s2g_ctx* ctx, const double* image, long long nx, long l
                          double* out)
 {
     dim3 grid((unsigned)((ny + 31) / 32), (unsigned)((nx + 31) / 32));
+    const int ph = s2g_phase_begin(ctx, PH_EPILOGUE);
     k_reduce2d<<<grid, 256, 0, ctx->stream>>>(image, nx, ny, n_images, reduce_image, out);
+    s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }
 

@@ -187,8 +187,11 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
     const int warps_needed = (int)std::min<long long>((P.n + 3) / 4, (long long)ctx->sm_count * 8 * 8);
     int blocks = max(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
+    const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
     k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, image, ctx->d_counters);
+    s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }
 
@@ -228,7 +231,10 @@ int s2g_launch_reduce_3d(s2g_ctx* ctx, const double* image, long long npix, int 
 {
     const long long ncell = npix * npix * npix;
     const int blocks = (int)std::min<long long>((ncell + 255) / 256, (long long)ctx->sm_count * 16);
+    const int ph = s2g_phase_begin(ctx, PH_EPILOGUE);
     k_reduce3d<<<max(blocks, 1), 256, 0, ctx->stream>>>(image, ncell, reduce_image, out);
+    s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }

@@ -51,6 +51,7 @@ struct s2g_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     int strategy = S2G_STRATEGY_AUTO;
+    int exact_norm = 0;  // 1: always sum pass A numerically (never use the closed-form kernel integral)
     s2g_stats stats{};
     long long host_pairs = 0;  // (tile,particle) pairs of the gather path, counted on the host
     std::map<std::string, s2g_buffer> pool;  // named scratch buffers, grow-only
@@ -58,7 +59,17 @@ struct s2g_ctx {
     // device-side counters (footprint pixels, touched, fallback, mapped, pairs ...)
     unsigned long long* d_counters = nullptr;  // 16 x u64
     unsigned long long* h_counters = nullptr;  // pinned mirror
+    // per-phase device timers: (phase, start, stop) event pairs recorded on the stream, summed in s2g_get_stats
+    struct timer { int phase; cudaEvent_t a, b; };
+    std::vector<timer> timers;
+    size_t timers_used = 0;
+    int launches = 0;  // kernels of this library launched since stats_begin (cub kernels counted as one each)
 };
+
+enum { PH_PREP = 0, PH_SORT = 1, PH_NORM = 2, PH_DEPOSIT = 3, PH_EPILOGUE = 4, PH_N = 5 };
+// records the start of a phase; returns a handle for s2g_phase_end
+int s2g_phase_begin(s2g_ctx* ctx, int phase);
+void s2g_phase_end(s2g_ctx* ctx, int handle);
 
 // returns a device scratch buffer of at least `bytes` (contents undefined); keeps it for reuse
 int s2g_scratch(s2g_ctx* ctx, const char* name, size_t bytes, void** out);

@@ -20,37 +20,98 @@ int s2g_launch_scatter_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
 
 namespace {
 
-constexpr int TILE = 64;       // tile edge in pixels
-constexpr int RPT = 16;        // rows per thread  (256 threads: 64 columns x 4 row groups x 16 rows)
+constexpr int TILE_W = 64;     // tile width  (j, the contiguous image axis): 2 warps side by side
+constexpr int RPT = 8;         // rows per thread
+constexpr int TILE_H = 4 * RPT;  // tile height (i): 4 row groups of RPT rows -> 256 threads
 constexpr int BATCH = 128;     // particle records staged in shared memory at a time
 constexpr int CHUNK = 2048;    // max pairs per work item
 
 struct __align__(16) GRec {
-    double x, y;          // pixel coordinates
-    double hinv;          // 1/h ; negative => "no pixel centre covered" branch (wk := 1 everywhere)
-    double h2lim;         // h^2 (1+1e-14): conservative pre-test for u <= 1
-    double an;            // area_norm
-    double dx_lo, dx_hi, dy_lo, dy_hi;  // edge overlaps
-    int iMin, iMax, jMin, jMax;
+    double x, y;          // pixel coordinates of the particle
+    double h, hinv;       // kernel support in pixels and its inverse
+    double an;            // area_norm (cic_2D.jl:188)
+    double dx_lo, dx_hi, dy_lo, dy_hi;  // overlap lengths of the first/last row and column (interior = 1)
+    int iMin, iMax, jMin, jMax;         // iMin > iMax: record not used (particle re-routed to the scatter kernel)
     int p;                // particle index (for the per-image quantity)
     int pad;
 };
 
-__device__ __forceinline__ int tile_count(const Rec2& r, int& ti0, int& ti1, int& tj0, int& tj1)
+// integral of the kernel shape over the unit disc, ∫ w(u) 2πu du = 1 / norm_2D(kernel)
+__host__ __device__ constexpr double shape_integral_2d(int kid)
 {
-    ti0 = r.iMin / TILE; ti1 = r.iMax / TILE; tj0 = r.jMin / TILE; tj1 = r.jMax / TILE;
-    return (ti1 - ti0 + 1) * (tj1 - tj0 + 1);
+    constexpr double pi = 3.14159265358979323846;
+    return kid == S2G_KERNEL_CUBIC         ? 7.0 * pi / 40.0
+           : kid == S2G_KERNEL_QUINTIC     ? 478.0 * pi / 15309.0
+           : kid == S2G_KERNEL_WENDLAND_C2 ? pi / 7.0
+           : kid == S2G_KERNEL_WENDLAND_C4 ? pi / 9.0
+           : kid == S2G_KERNEL_WENDLAND_C6 ? 7.0 * pi / 78.0
+                                           : 3.0 * pi / 8.0;
+}
+
+// smallest h [pixels] from which the discrete pass-A sum of an UNCLIPPED footprint equals h^2 * shape_integral to
+// better than 2e-13 relative (tools/analytic_norm_study.py; Poisson summation).  Infinity: never use the integral.
+__host__ __device__ constexpr double analytic_norm_min_h(int kid)
+{
+    return kid == S2G_KERNEL_WENDLAND_C8   ? 32.0
+           : kid == S2G_KERNEL_WENDLAND_C6 ? 48.0
+           : kid == S2G_KERNEL_WENDLAND_C4 ? 96.0
+           : kid == S2G_KERNEL_QUINTIC     ? 96.0
+                                           : 1e300;
+}
+
+// sqrt(s) for 0 <= s < ~4 to ~2 ulp: MUFU.RSQ64H seed + one third-order Newton step, no IEEE fix-up, no slow path
+__device__ __forceinline__ double sqrt_fast(double s)
+{
+    const double sg = fmax(s, 1e-280);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sg));
+    const double e = fma(-sg, y * y, 1.0);
+    const double c = fma(e, 0.375, 0.5);
+    return s * fma(c, e * y, y);
+}
+
+// kernel shape for 0 <= u < 1 WITHOUT the range test (callers mask u >= 1)
+template <int KID>
+__device__ __forceinline__ double shape_in(double u)
+{
+    const double t = 1.0 - u;
+    if (KID == S2G_KERNEL_CUBIC) {
+        const double a = fma(6.0 * (u - 1.0), u * u, 1.0), b = 2.0 * (t * t * t);
+        return u < 0.5 ? a : b;
+    } else if (KID == S2G_KERNEL_QUINTIC) {
+        const double b = fmax(2.0 / 3.0 - u, 0.0), c = fmax(1.0 / 3.0 - u, 0.0);
+        const double a2 = t * t, b2 = b * b, c2 = c * c;
+        return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a2 * a2 * t));
+    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
+        const double t2 = t * t;
+        return (t2 * t2) * fma(4.0, u, 1.0);
+    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
+        const double t2 = t * t;
+        return (t2 * t2 * t2) * fma(fma(35.0 / 3.0, u, 6.0), u, 1.0);
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        const double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4) * fma(fma(fma(32.0, u, 25.0), u, 8.0), u, 1.0);
+    } else {
+        const double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4 * t2) * fma(fma(fma(fma(429.0, u, 450.0), u, 210.0), u, 50.0), u, 5.0);
+    }
+}
+
+__device__ __forceinline__ bool nonzero_bits(double v)
+{
+    return ((__double2hiint(v) & 0x7fffffff) | __double2loint(v)) != 0;
 }
 
 // does the kernel support (circle of radius h around (x,y)) possibly reach a pixel centre of tile (ti,tj)?
-// conservative (never rejects a tile that holds a pixel with u <= 1); used identically by count and expand.
-__device__ __forceinline__ bool tile_hit(double x, double y, double h, int ti, int tj)
+// conservative (never rejects a tile that holds a pixel with u < 1); evaluated on the GRec fields by BOTH the pair
+// count (k_norm2d) and the pair expansion (k_expand), so the two always agree.
+__device__ __forceinline__ bool tile_hit(const GRec& g, int ti, int tj)
 {
-    const double lo_i = ti * (double)TILE + 0.5, hi_i = lo_i + (TILE - 1);
-    const double lo_j = tj * (double)TILE + 0.5, hi_j = lo_j + (TILE - 1);
-    const double ddx = fmax(fmax(lo_i - x, 0.0), x - hi_i);
-    const double ddy = fmax(fmax(lo_j - y, 0.0), y - hi_j);
-    const double hh = h * (1.0 + 1e-9) + 1e-9;
+    const double lo_i = ti * (double)TILE_H + 0.5, hi_i = lo_i + (TILE_H - 1);
+    const double lo_j = tj * (double)TILE_W + 0.5, hi_j = lo_j + (TILE_W - 1);
+    const double ddx = fmax(fmax(lo_i - g.x, 0.0), g.x - hi_i);
+    const double ddy = fmax(fmax(lo_j - g.y, 0.0), g.y - hi_j);
+    const double hh = g.h * (1.0 + 1e-9) + 1e-9;
     return ddx * ddx + ddy * ddy <= hh * hh;
 }
 
@@ -68,12 +129,8 @@ __global__ void __launch_bounds__(256) k_classify(s2g_particles P, s2g_geom G, l
         const long long fp = (long long)(r.iMax - r.iMin + 1) * (r.jMax - r.jMin + 1);
         const bool gather = force == S2G_STRATEGY_GATHER || (force == S2G_STRATEGY_AUTO && fp >= gather_min_pixels);
         c = gather ? 2 : 1;
-        if (gather) {
-            int ti0, ti1, tj0, tj1;
-            tile_count(r, ti0, ti1, tj0, tj1);
-            // pairs are counted after pass A (the fallback branch must keep every tile); upper bound here
-            np = (unsigned)((ti1 - ti0 + 1) * (tj1 - tj0 + 1));
-        }
+        if (gather)  // upper bound of the number of (tile, particle) pairs
+            np = (unsigned)((r.iMax / TILE_H - r.iMin / TILE_H + 1) * (r.jMax / TILE_W - r.jMin / TILE_W + 1));
     }
     cls[t] = c;
     npairs[t] = np;
@@ -91,15 +148,20 @@ __global__ void __launch_bounds__(256) k_build_lists(const int* __restrict__ cls
     if (c == 2) list_g[pos_g[t]] = (int)(p0 + t);
 }
 
-// ---- pass A for gather particles: one warp per particle, lanes along j, rows looped
+// ---- pass A for gather particles (cic_2D.jl:11-72): one warp per particle.
+// distr_weight = Σ w(u)·dA over the pixel centres inside the kernel.  Work in units of h: with a = (x-i-0.5)/h,
+// b = (y-j-0.5)/h a pixel is inside iff a²+b² < 1.  Lanes own columns, rows are walked four at a time (independent
+// dependency chains keep the FP64 pipe busy).  Unclipped, well-resolved footprints take the closed form
+// h²·∫w instead (analytic_norm_min_h).  Particles in the "no pixel centre covered" branch are re-routed to the
+// scatter kernel (they are tiny or clipped; their wk := 1 deposit does not fit the gather kernel's inner loop).
 template <int KID>
 __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, const int* __restrict__ list,
-                                                long long n_list, GRec* __restrict__ recs,
-                                                unsigned* __restrict__ npairs_g,
+                                                long long n_list, int exact_norm, GRec* __restrict__ recs,
+                                                unsigned* __restrict__ npairs_g, int* __restrict__ reroute,
                                                 unsigned long long* __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long fallback = 0, mapped = 0, fpx = 0;
+    unsigned long long mapped = 0, fpx = 0;
     for (;;) {
         long long t = 0;
         if (lane == 0) t = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
@@ -111,81 +173,86 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
         const int ni = r.iMax - r.iMin + 1, nj = r.jMax - r.jMin + 1;
         const double dx_lo = overlap_1d(r.x, r.h, r.iMin), dx_hi = overlap_1d(r.x, r.h, r.iMax);
         const double dy_lo = overlap_1d(r.y, r.h, r.jMin), dy_hi = overlap_1d(r.y, r.h, r.jMax);
-        const double h2lim = r.h * r.h * (1.0 + 1e-14);
-        double sw = 0.0;
-        int cnt = 0;
-        for (int jc = lane; jc < nj; jc += 32) {
-            const int j = r.jMin + jc;
-            const double yd = center_dist(r.y, (double)j);
-            const double yd2 = __dmul_rn(yd, yd);
-            const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
-            if (yd2 > h2lim) continue;
-            for (int ir = 0; ir < ni; ++ir) {
-                const int i = r.iMin + ir;
-                const double xd = center_dist(r.x, (double)i);
-                const double xd2 = __dmul_rn(xd, xd);
-                if (__dadd_rn(xd2, yd2) > h2lim) continue;
-                const double u = u_of(xd2, yd2, r.hinv);
-                if (u <= 1.0) {
-                    const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
-                    sw = fma(kernel_shape<KID>(u), dx * dy, sw);
-                    ++cnt;
-                }
-            }
-        }
-        sw = warp_sum(sw);
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        bool fb = false;
-        double n_distr, wpp;
-        if (sw == 0.0) {
-            fb = true;
-            double da = 0.0;
-            for (int jc = lane; jc < nj; jc += 32) {
-                const int j = r.jMin + jc;
-                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
-                for (int ir = 0; ir < ni; ++ir) {
-                    const int i = r.iMin + ir;
-                    const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
-                    da += dx * dy;
-                }
-            }
-            da = warp_sum(da);
-            n_distr = (double)ni * (double)nj;
-            wpp = (da != 0.0) ? n_distr / da : 1.0;
-            ++fallback;
+        const int n1 = (int)G.npix - 1;
+        // clipped by the image border?  (unclipped: the bounds are the plain floors of x±h)
+        const bool unclipped = floor_to_int(r.x - r.h) >= 0 && floor_to_int(r.x + r.h) <= n1 &&
+                               floor_to_int(r.y - r.h) >= 0 && floor_to_int(r.y + r.h) <= n1;
+        double sw;
+        long long cnt = 1;
+        if (!exact_norm && unclipped && r.h >= analytic_norm_min_h(KID)) {
+            sw = r.h * r.h * shape_integral_2d(KID);
         } else {
-            n_distr = (double)cnt;
-            wpp = n_distr / sw;
+            double acc = 0.0;
+            int c = 0;
+            const double xb = (r.x - (double)r.iMin - 0.5) * r.hinv;  // a of the first row
+            for (int jc = lane; jc < ((nj + 31) & ~31); jc += 32) {
+                const int j = r.jMin + jc;
+                const bool col = jc < nj;
+                const double b = center_dist(r.y, (double)j) * r.hinv;
+                const double b2 = col ? b * b : 4.0;
+                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+                // rows that can reach this 32-column group: a² < 1 - min_lanes(b²)
+                double m = b2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (m >= 1.0) continue;
+                const double reach = sqrt(1.0 - m) * r.h + 1.0;
+                const int r_lo = max(0, (int)floor(r.x - 0.5 - reach) - r.iMin);
+                const int r_hi = min(ni - 1, (int)ceil(r.x - 0.5 + reach) - r.iMin);
+                double colsum = 0.0;
+                for (int ir = r_lo; ir <= r_hi; ir += 4) {
+                    double wk[4];
+                    bool in[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double a = fma(-(double)(ir + k), r.hinv, xb);
+                        const double s = fma(a, a, b2);
+                        in[k] = (s < 1.0) && (ir + k <= r_hi);
+                        wk[k] = shape_in<KID>(sqrt_fast(s));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = r.iMin + ir + k;
+                        const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                        if (in[k]) { colsum = fma(wk[k], dx, colsum); ++c; }
+                    }
+                }
+                acc = fma(colsum, dy, acc);
+            }
+            sw = warp_sum(acc);
+            cnt = __reduce_add_sync(0xffffffffu, c);
         }
-        const double kernel_norm = r.area / n_distr;
-        const double area_norm = kernel_norm * wpp * r.w * r.dz;
-        // exact pair count (tiles the kernel support can reach; every bbox tile in the fallback branch)
-        int ti0, ti1, tj0, tj1;
-        tile_count(r, ti0, ti1, tj0, tj1);
-        const int nti = ti1 - ti0 + 1, ntj = tj1 - tj0 + 1;
+        GRec g;
+        g.x = r.x; g.y = r.y; g.h = r.h; g.hinv = r.hinv;
+        g.dx_lo = dx_lo; g.dx_hi = dx_hi; g.dy_lo = dy_lo; g.dy_hi = dy_hi;
+        g.iMin = r.iMin; g.iMax = r.iMax; g.jMin = r.jMin; g.jMax = r.jMax;
+        g.p = (int)p; g.pad = 0;
         unsigned np = 0;
-        for (int q = lane; q < nti * ntj; q += 32) {
-            const int ti = ti0 + q / ntj, tj = tj0 + q % ntj;
-            if (fb || tile_hit(r.x, r.y, r.h, ti, tj)) ++np;
+        if (sw == 0.0) {
+            // cic_2D.jl:51-66 branch -> scatter kernel
+            g.iMin = 1; g.iMax = 0; g.an = 0.0;
+            if (lane == 0) reroute[atomicAdd(&counters[CNT_PAIRS], 1ull)] = (int)p;
+        } else {
+            // kernel_norm * weight_per_pix = (area/N) * (N/sw); N cancels to rounding (cic_2D.jl:187-188)
+            const double n_distr = (double)cnt;
+            const double kernel_norm = r.area / n_distr;
+            g.an = kernel_norm * (n_distr / sw) * r.w * r.dz;
+            const int ti0 = r.iMin / TILE_H, tj0 = r.jMin / TILE_W;
+            const int nti = r.iMax / TILE_H - ti0 + 1, ntj = r.jMax / TILE_W - tj0 + 1;
+            for (int q = lane; q < nti * ntj; q += 32)
+                if (tile_hit(g, ti0 + q / ntj, tj0 + q % ntj)) ++np;
+            np = __reduce_add_sync(0xffffffffu, np);
+            if (lane == 0) {
+                ++mapped;
+                fpx += (unsigned long long)ni * (unsigned long long)nj;
+            }
         }
-        np = __reduce_add_sync(0xffffffffu, np);
         if (lane == 0) {
-            GRec g;
-            g.x = r.x; g.y = r.y;
-            g.hinv = fb ? -r.hinv : r.hinv;
-            g.h2lim = h2lim;
-            g.an = area_norm;
-            g.dx_lo = dx_lo; g.dx_hi = dx_hi; g.dy_lo = dy_lo; g.dy_hi = dy_hi;
-            g.iMin = r.iMin; g.iMax = r.iMax; g.jMin = r.jMin; g.jMax = r.jMax;
-            g.p = (int)p; g.pad = 0;
             recs[t] = g;
             npairs_g[t] = np;
-            ++mapped;
-            fpx += (unsigned long long)ni * (unsigned long long)nj;
         }
     }
     if (lane == 0) {
-        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
         if (mapped) { atomicAdd(&counters[CNT_MAPPED], mapped); atomicAdd(&counters[CNT_GATHER], mapped); }
         if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
     }
@@ -199,20 +266,18 @@ __global__ void __launch_bounds__(256) k_expand(const GRec* __restrict__ recs, c
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n_list) return;
     const GRec g = recs[t];
-    const bool fb = g.hinv < 0;
-    const double h = 1.0 / fabs(g.hinv);
-    const int ti0 = g.iMin / TILE, ti1 = g.iMax / TILE, tj0 = g.jMin / TILE, tj1 = g.jMax / TILE;
+    if (g.iMin > g.iMax) return;
+    const int ti0 = g.iMin / TILE_H, ti1 = g.iMax / TILE_H, tj0 = g.jMin / TILE_W, tj1 = g.jMax / TILE_W;
     unsigned o = off[t];
     for (int ti = ti0; ti <= ti1; ++ti)
         for (int tj = tj0; tj <= tj1; ++tj)
-            if (fb || tile_hit(g.x, g.y, h * (1.0 + 1e-12), ti, tj)) {
+            if (tile_hit(g, ti, tj)) {
                 keys[o] = (unsigned)(ti * ntile_j + tj);
                 vals[o] = (unsigned)t;
                 ++o;
             }
 }
 
-// tile_begin[k] .. tile_begin[k+1] after an exclusive scan of per-tile counts
 __global__ void __launch_bounds__(256) k_tile_hist(const unsigned* __restrict__ keys, long long m,
                                                    unsigned* __restrict__ tile_cnt)
 {
@@ -229,7 +294,10 @@ __global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict_
     nchunks[t] = (tile_cnt[t] + CHUNK - 1) / CHUNK;
 }
 
-// ---- the gather kernel
+// ---- the gather kernel: pass B (cic_2D.jl:193-222) without atomics.
+// A CTA owns a TILE_H x TILE_W tile for the duration of a work item (a chunk of the tile's particle list).  Thread
+// (rg, jl) owns the pixels (ibase + 0..RPT-1, j) and keeps their weight and quantity sums in registers; particle
+// records stream through shared memory.  One coalesced red.add flush per work item.
 template <int KID>
 __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
                                                      const unsigned* __restrict__ tile_begin,   // ntiles+1
@@ -244,9 +312,9 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
     __shared__ unsigned s_work[3];
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int jl = tid & (TILE - 1);         // column inside the tile
-    const int rg = tid >> 6;                 // row group 0..3
-    unsigned long long touched = 0;
+    const int jl = tid & (TILE_W - 1);       // column inside the tile
+    const int rg = tid / TILE_W;             // row group 0..3
+    unsigned touched = 0;
 
     for (;;) {
         if (tid == 0) {
@@ -268,10 +336,10 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
         __syncthreads();
         const unsigned tile = s_work[0], wb = s_work[1], we = s_work[2];
         if (tile == 0xffffffffu) break;
-        const int i0 = (int)(tile / ntile_j) * TILE, j0 = (int)(tile % ntile_j) * TILE;
+        const int i0 = (int)(tile / ntile_j) * TILE_H, j0 = (int)(tile % ntile_j) * TILE_W;
         const int j = j0 + jl;
         const int ibase = i0 + rg * RPT;
-        const double jd = (double)j;
+        const double jd = (double)j, id0 = (double)ibase;
 
         double acc_w[RPT], acc_q[RPT];
 #pragma unroll
@@ -291,38 +359,39 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
                 // warp-uniform row cull
                 const int rlo = max(g.iMin, ibase), rhi = min(g.iMax, ibase + RPT - 1);
                 if (rlo > rhi) continue;
-                const bool col_in = (j >= g.jMin) && (j <= g.jMax);
-                const bool fb = g.hinv < 0;
-                const double yd = center_dist(g.y, jd);
-                const double yd2 = __dmul_rn(yd, yd);
-                const bool col_live = col_in && (fb || yd2 <= g.h2lim);
-                if (!__any_sync(0xffffffffu, col_live)) continue;
+                const double hinv = g.hinv;
+                const double bq = center_dist(g.y, jd) * hinv;
+                const double b2 = bq * bq;
+                const bool live = (j >= g.jMin) && (j <= g.jMax) && (b2 < 1.0);
+                if (!__any_sync(0xffffffffu, live)) continue;
                 const double dy = (j == g.jMin) ? g.dy_lo : ((j == g.jMax) ? g.dy_hi : 1.0);
-                const double hinv = fabs(g.hinv);
                 const double dyan = dy * g.an;
                 const double q = s_q[e];
+                const double xb = center_dist(g.x, id0) * hinv;  // a of row ibase
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    const int i = ibase + r;
-                    if (i < rlo || i > rhi) continue;  // uniform
-                    if (!col_live) continue;
-                    const double xd = center_dist(g.x, (double)i);
-                    const double xd2 = __dmul_rn(xd, xd);
-                    double wk;
-                    if (fb)
-                        wk = 1.0;
-                    else {
-                        if (__dadd_rn(xd2, yd2) > g.h2lim) continue;
-                        const double u = u_of(xd2, yd2, hinv);
-                        if (!(u <= 1.0)) continue;
-                        wk = kernel_shape<KID>(u);
+                for (int r4 = 0; r4 < RPT; r4 += 4) {
+                    if (ibase + r4 > rhi || ibase + r4 + 3 < rlo) continue;  // uniform
+                    double s[4];
+                    bool in[4];
+                    bool any_in = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = ibase + r4 + k;
+                        const double a = fma(-(double)(r4 + k), hinv, xb);
+                        s[k] = fma(a, a, b2);
+                        in[k] = live && (s[k] < 1.0) && (i >= rlo) && (i <= rhi);
+                        any_in = any_in || in[k];
                     }
-                    const double dx = (i == g.iMin) ? g.dx_lo : ((i == g.iMax) ? g.dx_hi : 1.0);
-                    const double pw = wk * dx * dyan;
-                    if (pw != 0.0) {
-                        acc_w[r] += pw;
-                        acc_q[r] = fma(q, pw, acc_q[r]);
-                        ++touched;
+                    if (!__any_sync(0xffffffffu, any_in)) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = ibase + r4 + k;
+                        const double wk = shape_in<KID>(sqrt_fast(s[k]));
+                        const double dx = (i == g.iMin) ? g.dx_lo : ((i == g.iMax) ? g.dx_hi : 1.0);
+                        const double pw = in[k] ? wk * (dx * dyan) : 0.0;
+                        acc_w[r4 + k] += pw;
+                        acc_q[r4 + k] = fma(q, pw, acc_q[r4 + k]);
+                        touched += nonzero_bits(pw) ? 1u : 0u;
                     }
                 }
             }
@@ -340,27 +409,33 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
                 }
             }
         }
+        if (image_k == 0 && touched > 0x7f000000u) {  // keep the 32-bit per-thread counter from wrapping
+            atomicAdd(&counters[CNT_TOUCHED], (unsigned long long)touched);
+            touched = 0;
+        }
         __syncthreads();  // s_work reuse
     }
     if (image_k == 0) {
-        touched = (unsigned long long)warp_sum_ll((long long)touched);
-        if (lane == 0 && touched) atomicAdd(&counters[CNT_TOUCHED], touched);
+        unsigned long long tt = (unsigned long long)warp_sum_ll((long long)touched);
+        if (lane == 0 && tt) atomicAdd(&counters[CNT_TOUCHED], tt);
     }
 }
 
 struct KLaunch {
-    int (*norm)(s2g_ctx*, const s2g_particles&, const s2g_geom&, const int*, long long, GRec*, unsigned*);
+    int (*norm)(s2g_ctx*, const s2g_particles&, const s2g_geom&, const int*, long long, int, GRec*, unsigned*, int*);
     int (*gather)(s2g_ctx*, const GRec*, const unsigned*, const unsigned*, const unsigned*, int, int, unsigned,
                   const s2g_particles&, const s2g_geom&, int, double*);
 };
 
 template <int KID>
-int launch_norm(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list, long long n_list, GRec* recs,
-                unsigned* npairs_g)
+int launch_norm(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list, long long n_list,
+                int exact_norm, GRec* recs, unsigned* npairs_g, int* reroute)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_PAIRS, 0, sizeof(unsigned long long), ctx->stream));
     const int blocks = (int)std::min<long long>((n_list + 7) / 8, (long long)ctx->sm_count * 8);
-    k_norm2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, G, list, n_list, recs, npairs_g, ctx->d_counters);
+    k_norm2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, G, list, n_list, exact_norm, recs, npairs_g, reroute,
+                                                          ctx->d_counters);
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
 }
@@ -424,14 +499,20 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
     case S2G_KERNEL_WENDLAND_C8: K = make_klaunch<S2G_KERNEL_WENDLAND_C8>(); break;
     default: s2g_set_error("unknown kernel id %d", kernel); return S2G_EINVAL;
     }
-    if (ctx->strategy == S2G_STRATEGY_SCATTER)
-        return s2g_launch_scatter_2d(ctx, P, G, kernel, nullptr, P.n, image);
+    if (ctx->strategy == S2G_STRATEGY_SCATTER) {
+        const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
+        const int rc = s2g_launch_scatter_2d(ctx, P, G, kernel, nullptr, P.n, image);
+        s2g_phase_end(ctx, ph);
+        return rc;
+    }
 
     const long long gather_min = env_ll("S2G_GATHER_MIN_PIXELS", 1024);
     const long long batch_max = env_ll("S2G_BATCH_PARTICLES", 8LL << 20);
     const long long pair_cap = env_ll("S2G_PAIR_CAP", 512LL << 20);
-    const int ntile_j = (int)((G.npix + TILE - 1) / TILE);
-    const int ntiles = ntile_j * ntile_j;
+    const int exact_norm = (int)env_ll("S2G_EXACT_NORM", 0) || ctx->exact_norm;
+    const int ntile_j = (int)((G.npix + TILE_W - 1) / TILE_W);
+    const int ntile_i = (int)((G.npix + TILE_H - 1) / TILE_H);
+    const int ntiles = ntile_i * ntile_j;
     cudaStream_t st = ctx->stream;
 
     long long p0 = 0;
@@ -447,6 +528,7 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         S2G_TRY(s2g_scratch(ctx, "g_list_g", sizeof(int) * nb, &d_lg));
         S2G_TRY(s2g_scratch(ctx, "g_sum", sizeof(unsigned long long), &d_sum));
         const int blocks = (int)((nb + 255) / 256);
+        int ph = s2g_phase_begin(ctx, PH_PREP);
         S2G_CUDA(cudaMemsetAsync((int*)d_cls + nb, 0, sizeof(int), st));
         k_classify<<<blocks, 256, 0, st>>>(P, G, p0, nb, gather_min, ctx->strategy, (int*)d_cls, (unsigned*)d_np);
         S2G_CUDA(cudaGetLastError());
@@ -471,6 +553,8 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         S2G_CUDA(cudaMemcpyAsync(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         S2G_CUDA(cudaMemcpyAsync(&h_ub, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        s2g_phase_end(ctx, ph);
+        ctx->launches += 4;
         S2G_CUDA(cudaStreamSynchronize(st));
         if ((long long)h_ub > pair_cap && nb > 1024) {  // too many (tile,particle) pairs: shrink the slice, redo it
             batch = std::max<long long>(1024, nb / 2);
@@ -483,27 +567,48 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         k_build_lists<<<blocks, 256, 0, st>>>((const int*)d_cls, (const unsigned*)d_ps, (const unsigned*)d_pg, p0, nb,
                                               (int*)d_ls, (int*)d_lg);
         S2G_CUDA(cudaGetLastError());
+        ctx->launches += 1;
 
         // ---- scatter bin (small footprints)
-        if (n_s > 0) S2G_TRY(s2g_launch_scatter_2d(ctx, P, G, kernel, (const int*)d_ls, n_s, image));
+        if (n_s > 0) {
+            ph = s2g_phase_begin(ctx, PH_DEPOSIT);
+            S2G_TRY(s2g_launch_scatter_2d(ctx, P, G, kernel, (const int*)d_ls, n_s, image));
+            s2g_phase_end(ctx, ph);
+        }
 
         // ---- gather bin
         if (n_g > 0) {
-            void *d_recs, *d_npg, *d_off;
+            void *d_recs, *d_npg, *d_off, *d_rr;
+            S2G_TRY(s2g_scratch(ctx, "g_reroute", sizeof(int) * n_g, &d_rr));
             S2G_TRY(s2g_scratch(ctx, "g_recs", sizeof(GRec) * n_g, &d_recs));
             S2G_TRY(s2g_scratch(ctx, "g_npg", sizeof(unsigned) * (n_g + 1), &d_npg));
             S2G_TRY(s2g_scratch(ctx, "g_off", sizeof(unsigned) * (n_g + 1), &d_off));
             S2G_CUDA(cudaMemsetAsync((unsigned*)d_npg + n_g, 0, sizeof(unsigned), st));
-            S2G_TRY(K.norm(ctx, P, G, (const int*)d_lg, n_g, (GRec*)d_recs, (unsigned*)d_npg));
+            ph = s2g_phase_begin(ctx, PH_NORM);
+            S2G_TRY(K.norm(ctx, P, G, (const int*)d_lg, n_g, exact_norm, (GRec*)d_recs, (unsigned*)d_npg,
+                           (int*)d_rr));
+            s2g_phase_end(ctx, ph);
+            ctx->launches += 1;
+            ph = s2g_phase_begin(ctx, PH_SORT);
             size_t tb4 = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb4, (const unsigned*)d_npg, (unsigned*)d_off, (int)(n_g + 1), st);
             S2G_TRY(s2g_scratch(ctx, "g_tmp", tb4 + 16, &d_tmp));
             S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb4, (const unsigned*)d_npg, (unsigned*)d_off,
                                                    (int)(n_g + 1), st));
             unsigned h_m = 0;
+            unsigned long long h_rr = 0;
             S2G_CUDA(cudaMemcpyAsync(&h_m, (unsigned*)d_off + n_g, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            S2G_CUDA(cudaMemcpyAsync(&h_rr, ctx->d_counters + CNT_PAIRS, sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, st));
             S2G_CUDA(cudaStreamSynchronize(st));
             const long long m = h_m;
+            if (h_rr > 0) {  // "no pixel centre covered" particles found by pass A -> scatter kernel
+                s2g_phase_end(ctx, ph);
+                ph = s2g_phase_begin(ctx, PH_DEPOSIT);
+                S2G_TRY(s2g_launch_scatter_2d(ctx, P, G, kernel, (const int*)d_rr, (long long)h_rr, image));
+                s2g_phase_end(ctx, ph);
+                ph = s2g_phase_begin(ctx, PH_SORT);
+            }
             if (m > 0) {
                 void *d_keys, *d_vals, *d_keys2, *d_vals2, *d_tcnt, *d_tbeg, *d_nch, *d_cbeg;
                 S2G_TRY(s2g_scratch(ctx, "g_keys", sizeof(unsigned) * m, &d_keys));
@@ -544,12 +649,19 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
                 unsigned h_chunks = 0;
                 S2G_CUDA(cudaMemcpyAsync(&h_chunks, (unsigned*)d_cbeg + ntiles, sizeof(unsigned),
                                          cudaMemcpyDeviceToHost, st));
+                s2g_phase_end(ctx, ph);
+                ph = -1;
+                ctx->launches += 8;
                 S2G_CUDA(cudaStreamSynchronize(st));
+                const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
                 for (int k = 0; k < G.n_images; ++k)
                     S2G_TRY(K.gather(ctx, (const GRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
                                      (const unsigned*)d_cbeg, ntiles, ntile_j, h_chunks, P, G, k, image));
+                s2g_phase_end(ctx, phg);
+                ctx->launches += G.n_images;
                 ctx->host_pairs += m;
             }
+            if (ph >= 0) s2g_phase_end(ctx, ph);
         }
         p0 += nb;
     }

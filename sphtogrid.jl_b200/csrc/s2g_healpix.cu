@@ -391,8 +391,11 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const HpGeom g = make_hp(nside);
     int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 8);
+    const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
     k_healpix<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, g, calc_mean, amap, wmap, ctx->d_counters);
+    s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }
 

@@ -90,6 +90,7 @@ int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const
     else
         k_stencil<3, 3><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image);
     S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return S2G_OK;
 }
 
