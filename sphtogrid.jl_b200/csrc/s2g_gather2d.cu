@@ -27,12 +27,13 @@ constexpr int BATCH = 128;     // particle records staged in shared memory at a 
 constexpr int CHUNK = 2048;    // max pairs per work item
 
 struct __align__(16) GRec {
-    double x, y;          // pixel coordinates of the particle
-    double h, hinv;       // kernel support in pixels and its inverse
-    double an;            // area_norm (cic_2D.jl:188)
-    double dx_lo, dx_hi, dy_lo, dy_hi;  // overlap lengths of the first/last row and column (interior = 1)
-    int iMin, iMax, jMin, jMax;         // iMin > iMax: record not used (particle re-routed to the scatter kernel)
-    int p;                // particle index (for the per-image quantity)
+    int iMin, iMax, jMin, jMax;  // footprint; iMin > iMax: record unused (particle re-routed to the scatter kernel)
+    double x, y;                 // pixel coordinates of the particle
+    double hinv, an;             // 1/h [1/pixel], area_norm (cic_2D.jl:188)
+    double dx_lo, dx_hi;         // overlap lengths of the first / last row    (interior rows: 1)
+    double dy_lo, dy_hi;         //                     first / last column
+    double h;
+    int p;                       // particle index (for the per-image quantity)
     int pad;
 };
 
@@ -59,42 +60,61 @@ __host__ __device__ constexpr double analytic_norm_min_h(int kid)
                                            : 1e300;
 }
 
-// sqrt(s) for 0 <= s < ~4 to ~2 ulp: MUFU.RSQ64H seed + one third-order Newton step, no IEEE fix-up, no slow path
-__device__ __forceinline__ double sqrt_fast(double s)
+// 1/sqrt(s) for s > 0 to ~2 ulp: MUFU.RSQ64H seed + one third-order Newton step (no IEEE fix-up, no slow path)
+__device__ __forceinline__ double rsqrt_fast(double s)
 {
-    const double sg = fmax(s, 1e-280);
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sg));
-    const double e = fma(-sg, y * y, 1.0);
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double e = fma(-s, y * y, 1.0);
     const double c = fma(e, 0.375, 0.5);
-    return s * fma(c, e * y, y);
+    return fma(c, e * y, y);
 }
 
-// kernel shape for 0 <= u < 1 WITHOUT the range test (callers mask u >= 1)
+// kernel shape as a function of t = 1 - u for 0 < t <= 1, WITHOUT range test (callers mask u >= 1).
+// The polynomial factor of the Wendland kernels is re-expanded in t (saves forming u); WendlandC8 keeps the u form
+// (its t-expansion has alternating coefficients ~4e3 and would lose ~3 digits to cancellation).
 template <int KID>
-__device__ __forceinline__ double shape_in(double u)
+__device__ __forceinline__ double shape_t(double t)
 {
-    const double t = 1.0 - u;
     if (KID == S2G_KERNEL_CUBIC) {
-        const double a = fma(6.0 * (u - 1.0), u * u, 1.0), b = 2.0 * (t * t * t);
-        return u < 0.5 ? a : b;
+        // u < 0.5: 1 + 6(u-1)u^2 = 1 - 6t + 12t^2 - 6t^3 ; else 2 t^3
+        const double a = fma(fma(fma(-6.0, t, 12.0), t, -6.0), t, 1.0), b = 2.0 * (t * t * t);
+        return t > 0.5 ? a : b;
     } else if (KID == S2G_KERNEL_QUINTIC) {
-        const double b = fmax(2.0 / 3.0 - u, 0.0), c = fmax(1.0 / 3.0 - u, 0.0);
+        const double b = fmax(t - 1.0 / 3.0, 0.0), c = fmax(t - 2.0 / 3.0, 0.0);
         const double a2 = t * t, b2 = b * b, c2 = c * c;
         return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a2 * a2 * t));
     } else if (KID == S2G_KERNEL_WENDLAND_C2) {
         const double t2 = t * t;
-        return (t2 * t2) * fma(4.0, u, 1.0);
+        return (t2 * t2) * fma(-4.0, t, 5.0);
     } else if (KID == S2G_KERNEL_WENDLAND_C4) {
         const double t2 = t * t;
-        return (t2 * t2 * t2) * fma(fma(35.0 / 3.0, u, 6.0), u, 1.0);
+        return (t2 * t2 * t2) * fma(fma(35.0 / 3.0, t, -88.0 / 3.0), t, 56.0 / 3.0);
     } else if (KID == S2G_KERNEL_WENDLAND_C6) {
         const double t2 = t * t, t4 = t2 * t2;
-        return (t4 * t4) * fma(fma(fma(32.0, u, 25.0), u, 8.0), u, 1.0);
+        return (t4 * t4) * fma(fma(fma(-32.0, t, 121.0), t, -154.0), t, 66.0);
     } else {
-        const double t2 = t * t, t4 = t2 * t2;
+        const double t2 = t * t, t4 = t2 * t2, u = 1.0 - t;
         return (t4 * t4 * t2) * fma(fma(fma(fma(429.0, u, 450.0), u, 210.0), u, 50.0), u, 5.0);
     }
+}
+
+// w(sqrt(s)) for 0 < s < 1 (garbage for s >= 1: mask it): t = 1 - s * rsqrt(s)
+template <int KID>
+__device__ __forceinline__ double shape_s(double s)
+{
+    return shape_t<KID>(fma(-s, rsqrt_fast(s), 1.0));
+}
+
+// v if flag else +0.0, as a data select (keeps the four per-group dependency chains in one straight-line block;
+// a C++ ?: around the kernel evaluation invites the compiler to branch around it per lane)
+__device__ __forceinline__ double select_or_zero(bool flag, double v)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
+        : "=d"(r)
+        : "d"(v), "r"((int)flag));
+    return r;
 }
 
 __device__ __forceinline__ bool nonzero_bits(double v)
@@ -200,21 +220,31 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
                 const int r_lo = max(0, (int)floor(r.x - 0.5 - reach) - r.iMin);
                 const int r_hi = min(ni - 1, (int)ceil(r.x - 0.5 + reach) - r.iMin);
                 double colsum = 0.0;
+                const double b2s = fmax(b2, 1e-300);  // keeps s > 0 when a pixel centre sits on the particle
                 for (int ir = r_lo; ir <= r_hi; ir += 4) {
                     double wk[4];
                     bool in[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const double a = fma(-(double)(ir + k), r.hinv, xb);
-                        const double s = fma(a, a, b2);
+                        const double s = fma(a, a, b2s);
                         in[k] = (s < 1.0) && (ir + k <= r_hi);
-                        wk[k] = shape_in<KID>(sqrt_fast(s));
+                        wk[k] = shape_s<KID>(s);
                     }
+                    if (ir == 0 || ir + 3 >= ni - 1) {  // group touches the first / last row: partial overlaps
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = r.iMin + ir + k;
-                        const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
-                        if (in[k]) { colsum = fma(wk[k], dx, colsum); ++c; }
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = r.iMin + ir + k;
+                            const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                            colsum = fma(select_or_zero(in[k], wk[k]), dx, colsum);
+                            c += in[k] ? 1 : 0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            colsum += select_or_zero(in[k], wk[k]);
+                            c += in[k] ? 1 : 0;
+                        }
                     }
                 }
                 acc = fma(colsum, dy, acc);
@@ -278,29 +308,37 @@ __global__ void __launch_bounds__(256) k_expand(const GRec* __restrict__ recs, c
             }
 }
 
-__global__ void __launch_bounds__(256) k_tile_hist(const unsigned* __restrict__ keys, long long m,
-                                                   unsigned* __restrict__ tile_cnt)
+// tile ranges of the sorted pair list by boundary detection (no atomics): [tile_beg[t], tile_end[t])
+__global__ void __launch_bounds__(256) k_tile_bounds(const unsigned* __restrict__ keys, long long m,
+                                                     unsigned* __restrict__ tile_beg, unsigned* __restrict__ tile_end)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= m) return;
-    atomicAdd(&tile_cnt[keys[t]], 1u);
+    const unsigned k = keys[t];
+    if (t == 0 || keys[t - 1] != k) tile_beg[k] = (unsigned)t;
+    if (t == m - 1 || keys[t + 1] != k) tile_end[k] = (unsigned)(t + 1);
 }
 
-__global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict__ tile_cnt, int ntiles,
+__global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict__ tile_beg,
+                                                     const unsigned* __restrict__ tile_end, int ntiles,
                                                      unsigned* __restrict__ nchunks)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
-    nchunks[t] = (tile_cnt[t] + CHUNK - 1) / CHUNK;
+    nchunks[t] = (tile_end[t] - tile_beg[t] + CHUNK - 1) / CHUNK;
 }
 
 // ---- the gather kernel: pass B (cic_2D.jl:193-222) without atomics.
-// A CTA owns a TILE_H x TILE_W tile for the duration of a work item (a chunk of the tile's particle list).  Thread
-// (rg, jl) owns the pixels (ibase + 0..RPT-1, j) and keeps their weight and quantity sums in registers; particle
-// records stream through shared memory.  One coalesced red.add flush per work item.
+// A CTA owns a TILE_H x TILE_W tile for the duration of a work item (a chunk of the tile's particle list).  Every
+// thread owns RPT pixels of the tile and keeps their weight and quantity sums in registers; particle records stream
+// through shared memory.  One coalesced red.add flush per work item.
+// Lane layout: a warp covers 16 columns x 2 interleaved rows (half-warp rows halve the idle lanes at the two ends
+// of each chord of the kernel disc compared with 32-wide rows); warp w: column group w&3, row block w>>2;
+// thread rows: i = i0 + (w>>2)*2*RPT + 2*r + (lane>>4), r = 0..RPT-1.
 template <int KID>
 __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
-                                                     const unsigned* __restrict__ tile_begin,   // ntiles+1
+                                                     const unsigned* __restrict__ tile_beg,
+                                                     const unsigned* __restrict__ tile_end,
                                                      const unsigned* __restrict__ chunk_begin,  // ntiles+1
                                                      int ntiles, int ntile_j, unsigned total_chunks,
                                                      const void* __restrict__ binq, int in_dtype, int n_images,
@@ -311,9 +349,10 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
     __shared__ double s_q[BATCH];
     __shared__ unsigned s_work[3];
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int jl = tid & (TILE_W - 1);       // column inside the tile
-    const int rg = tid / TILE_W;             // row group 0..3
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    const int jl = (wq & 3) * 16 + (lane & 15);   // column inside the tile
+    const int rpar = lane >> 4;                   // row parity inside the warp
+    const int rblk = (wq >> 2) * (2 * RPT);       // first row of the warp's row block
     unsigned touched = 0;
 
     for (;;) {
@@ -328,8 +367,8 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
                 }
                 tile = (unsigned)lo;
                 const unsigned c = w - chunk_begin[lo];
-                b = tile_begin[lo] + c * CHUNK;
-                e = min(b + CHUNK, tile_begin[lo + 1]);
+                b = tile_beg[lo] + c * CHUNK;
+                e = min(b + CHUNK, tile_end[lo]);
             }
             s_work[0] = tile; s_work[1] = b; s_work[2] = e;
         }
@@ -338,7 +377,9 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
         if (tile == 0xffffffffu) break;
         const int i0 = (int)(tile / ntile_j) * TILE_H, j0 = (int)(tile % ntile_j) * TILE_W;
         const int j = j0 + jl;
-        const int ibase = i0 + rg * RPT;
+        const int jw0 = j0 + (wq & 3) * 16;   // first column of this warp (uniform)
+        const int wbase = i0 + rblk;          // first row of this warp (uniform)
+        const int ibase = wbase + rpar;       // first row of this thread; its rows are ibase + 2r
         const double jd = (double)j, id0 = (double)ibase;
 
         double acc_w[RPT], acc_q[RPT];
@@ -356,52 +397,73 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
             __syncthreads();
             for (int e = 0; e < nb; ++e) {
                 const GRec& g = s_rec[e];
-                // warp-uniform row cull
-                const int rlo = max(g.iMin, ibase), rhi = min(g.iMax, ibase + RPT - 1);
-                if (rlo > rhi) continue;
+                // warp-uniform integer culls: the warp's 16 rows x 16 columns against the footprint box
+                const int rlo = max(g.iMin, wbase), rhi = min(g.iMax, wbase + 2 * RPT - 1);
+                if (rlo > rhi || g.jMax < jw0 || g.jMin > jw0 + 15) continue;
                 const double hinv = g.hinv;
                 const double bq = center_dist(g.y, jd) * hinv;
-                const double b2 = bq * bq;
-                const bool live = (j >= g.jMin) && (j <= g.jMax) && (b2 < 1.0);
-                if (!__any_sync(0xffffffffu, live)) continue;
+                const double b2 = fmax(bq * bq, 1e-300);  // s > 0 even when a pixel centre sits on the particle
                 const double dy = (j == g.jMin) ? g.dy_lo : ((j == g.jMax) ? g.dy_hi : 1.0);
                 const double dyan = dy * g.an;
-                const double q = s_q[e];
-                const double xb = center_dist(g.x, id0) * hinv;  // a of row ibase
+                // pix_weight != 0 test of cic_2D.jl:211 hoisted: wk > 0 inside the disc, so only dy*area_norm decides
+                const bool live = (j >= g.jMin) && (j <= g.jMax) && (b2 < 1.0) && nonzero_bits(dyan);
+                if (!__any_sync(0xffffffffu, live)) continue;
+                const double dyanq = dyan * s_q[e];
+                const double xb = center_dist(g.x, id0) * hinv;  // a of this thread's first row
+                const double hinv2 = hinv + hinv;
 #pragma unroll
                 for (int r4 = 0; r4 < RPT; r4 += 4) {
-                    if (ibase + r4 > rhi || ibase + r4 + 3 < rlo) continue;  // uniform
+                    const int g_lo = wbase + 2 * r4, g_hi = g_lo + 7;  // rows of this group (both parities)
+                    if (g_lo > rhi || g_hi < rlo) continue;            // uniform
                     double s[4];
                     bool in[4];
                     bool any_in = false;
+                    const bool interior = (g_lo > g.iMin) && (g_hi < g.iMax);  // uniform: no first/last row inside
+                    if (interior) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = ibase + r4 + k;
-                        const double a = fma(-(double)(r4 + k), hinv, xb);
-                        s[k] = fma(a, a, b2);
-                        in[k] = live && (s[k] < 1.0) && (i >= rlo) && (i <= rhi);
-                        any_in = any_in || in[k];
-                    }
-                    if (!__any_sync(0xffffffffu, any_in)) continue;
+                        for (int k = 0; k < 4; ++k) {
+                            const double a = fma(-(double)(r4 + k), hinv2, xb);
+                            s[k] = fma(a, a, b2);
+                            in[k] = live && (s[k] < 1.0);
+                            any_in = any_in || in[k];
+                        }
+                        if (!__any_sync(0xffffffffu, any_in)) continue;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = ibase + r4 + k;
-                        const double wk = shape_in<KID>(sqrt_fast(s[k]));
-                        const double dx = (i == g.iMin) ? g.dx_lo : ((i == g.iMax) ? g.dx_hi : 1.0);
-                        const double pw = in[k] ? wk * (dx * dyan) : 0.0;
-                        acc_w[r4 + k] += pw;
-                        acc_q[r4 + k] = fma(q, pw, acc_q[r4 + k]);
-                        touched += nonzero_bits(pw) ? 1u : 0u;
+                        for (int k = 0; k < 4; ++k) {
+                            const double wk = select_or_zero(in[k], shape_s<KID>(s[k]));
+                            acc_w[r4 + k] = fma(wk, dyan, acc_w[r4 + k]);
+                            acc_q[r4 + k] = fma(wk, dyanq, acc_q[r4 + k]);
+                            touched += in[k] ? 1u : 0u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = ibase + 2 * (r4 + k);
+                            const double a = fma(-(double)(r4 + k), hinv2, xb);
+                            s[k] = fma(a, a, b2);
+                            in[k] = live && (s[k] < 1.0) && (i >= g.iMin) && (i <= g.iMax);
+                            any_in = any_in || in[k];
+                        }
+                        if (!__any_sync(0xffffffffu, any_in)) continue;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = ibase + 2 * (r4 + k);
+                            const double dx = (i == g.iMin) ? g.dx_lo : ((i == g.iMax) ? g.dx_hi : 1.0);
+                            const double wk = select_or_zero(in[k], shape_s<KID>(s[k]) * dx);
+                            acc_w[r4 + k] = fma(wk, dyan, acc_w[r4 + k]);
+                            acc_q[r4 + k] = fma(wk, dyanq, acc_q[r4 + k]);
+                            touched += (in[k] && nonzero_bits(dx)) ? 1u : 0u;
+                        }
                     }
                 }
             }
         }
-        // flush: coalesced along j
+        // flush: each half-warp writes 16 consecutive doubles (128 B) of one image row
         const long long npl = npix * npix;
         if (j < npix) {
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
-                const int i = ibase + r;
+                const int i = ibase + 2 * r;
                 if (i < npix && (acc_w[r] != 0.0 || acc_q[r] != 0.0)) {
                     const long long idx = (long long)i * npix + j;
                     if (image_k == 0) red_add(image + npl * n_images + idx, acc_w[r]);
@@ -423,8 +485,8 @@ __global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ re
 
 struct KLaunch {
     int (*norm)(s2g_ctx*, const s2g_particles&, const s2g_geom&, const int*, long long, int, GRec*, unsigned*, int*);
-    int (*gather)(s2g_ctx*, const GRec*, const unsigned*, const unsigned*, const unsigned*, int, int, unsigned,
-                  const s2g_particles&, const s2g_geom&, int, double*);
+    int (*gather)(s2g_ctx*, const GRec*, const unsigned*, const unsigned*, const unsigned*, const unsigned*, int, int,
+                  unsigned, const s2g_particles&, const s2g_geom&, int, double*);
 };
 
 template <int KID>
@@ -441,13 +503,13 @@ int launch_norm(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const i
 }
 
 template <int KID>
-int launch_gather(s2g_ctx* ctx, const GRec* recs, const unsigned* vals, const unsigned* tile_begin,
-                  const unsigned* chunk_begin, int ntiles, int ntile_j, unsigned total_chunks, const s2g_particles& P,
-                  const s2g_geom& G, int image_k, double* image)
+int launch_gather(s2g_ctx* ctx, const GRec* recs, const unsigned* vals, const unsigned* tile_beg,
+                  const unsigned* tile_end, const unsigned* chunk_begin, int ntiles, int ntile_j, unsigned total_chunks,
+                  const s2g_particles& P, const s2g_geom& G, int image_k, double* image)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * 2);
-    k_gather2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_begin, chunk_begin, ntiles, ntile_j,
+    k_gather2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles, ntile_j,
                                                             total_chunks, P.binq, P.in_dtype, G.n_images, image_k,
                                                             G.npix, image, ctx->d_counters);
     S2G_CUDA(cudaGetLastError());
@@ -632,18 +694,18 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
                                                          (const unsigned*)d_vals, (unsigned*)d_vals2, (int)m, 0, bits,
                                                          st));
                 S2G_CUDA(cudaMemsetAsync(d_tcnt, 0, sizeof(unsigned) * (ntiles + 1), st));
-                k_tile_hist<<<(int)((m + 255) / 256), 256, 0, st>>>((const unsigned*)d_keys2, m, (unsigned*)d_tcnt);
+                S2G_CUDA(cudaMemsetAsync(d_tbeg, 0, sizeof(unsigned) * (ntiles + 1), st));
+                k_tile_bounds<<<(int)((m + 255) / 256), 256, 0, st>>>((const unsigned*)d_keys2, m, (unsigned*)d_tbeg,
+                                                                      (unsigned*)d_tcnt);
                 S2G_CUDA(cudaGetLastError());
                 S2G_CUDA(cudaMemsetAsync(d_nch, 0, sizeof(unsigned) * (ntiles + 1), st));
-                k_tile_chunks<<<(ntiles + 255) / 256, 256, 0, st>>>((const unsigned*)d_tcnt, ntiles, (unsigned*)d_nch);
+                k_tile_chunks<<<(ntiles + 255) / 256, 256, 0, st>>>((const unsigned*)d_tbeg, (const unsigned*)d_tcnt,
+                                                                    ntiles, (unsigned*)d_nch);
                 S2G_CUDA(cudaGetLastError());
                 size_t tb3 = 0;
-                cub::DeviceScan::ExclusiveSum(nullptr, tb3, (const unsigned*)d_tcnt, (unsigned*)d_tbeg, ntiles + 1, st);
+                cub::DeviceScan::ExclusiveSum(nullptr, tb3, (const unsigned*)d_nch, (unsigned*)d_cbeg, ntiles + 1, st);
                 S2G_TRY(s2g_scratch(ctx, "g_tmp", tb3 + 16, &d_tmp));
                 size_t tbb = tb3 + 16;
-                S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tbb, (const unsigned*)d_tcnt, (unsigned*)d_tbeg,
-                                                       ntiles + 1, st));
-                tbb = tb3 + 16;
                 S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tbb, (const unsigned*)d_nch, (unsigned*)d_cbeg,
                                                        ntiles + 1, st));
                 unsigned h_chunks = 0;
@@ -656,7 +718,8 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
                 const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
                 for (int k = 0; k < G.n_images; ++k)
                     S2G_TRY(K.gather(ctx, (const GRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
-                                     (const unsigned*)d_cbeg, ntiles, ntile_j, h_chunks, P, G, k, image));
+                                     (const unsigned*)d_tcnt, (const unsigned*)d_cbeg, ntiles, ntile_j, h_chunks, P,
+                                     G, k, image));
                 s2g_phase_end(ctx, phg);
                 ctx->launches += G.n_images;
                 ctx->host_pairs += m;
