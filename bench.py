@@ -31,13 +31,19 @@ WORKLOADS = {
                desc="synthetic 16M-particle box, 2D calc_mean mass-weighted T map, 4096^2, WendlandC6"),
     "c3": dict(n=64 * 1024 * 1024, npix=512, dims=3, kernel="Cubic", n_ngb=64.0, seed=3,
                desc="synthetic 64M particles, 3D sphMapping onto 512^3, Cubic"),
+    "c4": dict(n=128 * 1024 * 1024, npix=2048, dims=0, kernel="WendlandC4", n_ngb=200.0, seed=4,
+               desc="synthetic 128M particles, healpix_map all-sky Nside=2048, WendlandC4, shell [0.05L,0.5L]"),
+    "c4s": dict(n=4 * 1024 * 1024, npix=2048, dims=0, kernel="WendlandC4", n_ngb=200.0, seed=4,
+                desc="4M particles of the c4 stream (hsml of the 128M set), Nside=2048 (debug)", n_stream=128 * 1024 * 1024),
+    "c3s": dict(n=8 * 1024 * 1024, npix=512, dims=3, kernel="Cubic", n_ngb=64.0, seed=3,
+                desc="8M particles of the c3 stream, 512^3 (debug)", n_stream=64 * 1024 * 1024),
     "c5": dict(n=1024 * 1024 * 1024, npix=8192, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=5,
                desc="synthetic 1B-particle box, 8192^2 2D map, WendlandC6"),
     "small": dict(n=1 << 20, npix=1024, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=2,
                   desc="1M particles, 1024^2 (debug)"),
 }
 SIGMA = 1.5
-KERNEL_DIM = {2: 2, 3: 3}
+KERNEL_DIM = {2: 2, 3: 3, 0: 2}
 
 
 def peaks():
@@ -210,20 +216,39 @@ def main():
     d_pos = torch.empty(n_loc * 3, dtype=f64, device=dev)
     d_h, d_m, d_rho, d_T = (torch.empty(n_loc, dtype=f64, device=dev) for _ in range(4))
     P = lambda t: _lib.ptr(t.data_ptr())
-    _lib.check(L.s2g_synth_particles_dev(ctx.handle, wl["seed"], s, n_loc, n_total, 1.0, wl["n_ngb"], SIGMA, 1,
-                                         P(d_pos), P(d_h), P(d_m), P(d_rho), P(d_T)))
+    _lib.check(L.s2g_synth_particles_dev(ctx.handle, wl["seed"], s, n_loc, wl.get("n_stream", n_total), 1.0,
+                                         wl["n_ngb"], SIGMA, 1, P(d_pos), P(d_h), P(d_m), P(d_rho), P(d_T)))
     d_one = torch.ones(n_loc, dtype=f64, device=dev) if dims == 3 else None
     par = s2g.mappingParameters(center=[0.5, 0.5, 0.5], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=npix)
     par2 = s2g.recentred_parameters(par)
     kid = getattr(s2g, wl["kernel"])(KERNEL_DIM[dims]).kernel_id
-    ncell = npix ** dims
+    healpix = dims == 0
+    if healpix:
+        # observer at the box centre; shell filter of filter_sort_particles done once, untimed, with torch ops
+        # (all particles that pass are handed to the deposit; the reference's sorted[mask] quirk is host logic)
+        rel = d_pos.view(n_loc, 3) - 0.5
+        rad = rel.norm(dim=1)
+        keep = (rad >= 0.05) & (rad <= 0.5)
+        d_pos = rel[keep].contiguous().view(-1)
+        d_h, d_m, d_rho, d_T = (t[keep].contiguous() for t in (d_h, d_m, d_rho, d_T))
+        n_loc = int(keep.sum())
+        del rel, rad, keep
+    ncell = npix ** dims if not healpix else 12 * npix * npix
     planes = 2
     image = torch.empty(ncell * planes, dtype=f64, device=dev)
     out = torch.empty(ncell, dtype=f64, device=dev)
-    q_t, w_t = (d_T, d_rho) if dims == 2 else (d_rho, d_one)
+    q_t, w_t = (d_T, d_rho) if dims != 3 else (d_rho, d_one)
     shift, half = _lib.dbl3(par.center), _lib.dbl3(par2.halfsize)
 
+    def step_healpix():
+        _lib.check(L.s2g_healpix_deposit_dev(ctx.handle, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1,
+                                             npix, kid, 1, 0, P(image), P(image[ncell:])))
+        if world > 1:
+            dist.all_reduce(image)
+
     def step_device():
+        if healpix:
+            return step_healpix()
         _lib.check(L.s2g_sphmap_dev(ctx.handle, dims, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1, 1,
                                     shift, 0, -1.0, half, float(par2.len2pix), npix, kid, 1, 0, P(image)))
         if world > 1:
@@ -262,9 +287,12 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step, wall_step = timed(step_device, args.steps, args.warmup, sampler)
-    st = ctx.stats()  # stats of the last library call... (reduce) -> re-run one deposit for the phase breakdown
-    _lib.check(L.s2g_sphmap_dev(ctx.handle, dims, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1, 1,
-                                shift, 0, -1.0, half, float(par2.len2pix), npix, kid, 1, 0, P(image)))
+    # stats of one more deposit (the last library call of a step is the reduce) for the phase breakdown
+    if healpix:
+        step_healpix()
+    else:
+        _lib.check(L.s2g_sphmap_dev(ctx.handle, dims, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1, 1,
+                                    shift, 0, -1.0, half, float(par2.len2pix), npix, kid, 1, 0, P(image)))
     st = ctx.stats()
     cnt = torch.tensor([st["n_mapped"], st["footprint_pixels"], st["touched_pixels"], st["n_pairs"],
                         st["n_launches"] + 1], dtype=f64, device=dev)
@@ -275,7 +303,7 @@ def main():
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the reduced map, all inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not healpix:
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
         h_pos, h_h, h_m, h_rho, h_q, h_w = pin(d_pos), pin(d_h), pin(d_m), pin(d_rho), pin(q_t), pin(w_t)
         h_out = torch.empty(ncell, dtype=f64, pin_memory=True)
@@ -311,12 +339,12 @@ def main():
         fp64_peak = r.value  # GFLOP/s, DFMA microbenchmark, same process, same clocks
         _lib.check(L.s2g_microbench(ctx.handle, 1, 256 << 20, 2000, C.byref(r)))
         red_peak = r.value   # Gred/s, 32 consecutive doubles per warp
-        flop_per_px = 40.0 if dims == 2 else 45.0   # SURVEY §8d roof 3: pass A + pass B per footprint pixel
+        flop_per_px = {2: 40.0, 3: 45.0, 0: 80.0}[dims]   # SURVEY §8d roof 3: pass A + pass B per footprint pixel
         fp64_ach = fpx * flop_per_px / (dep_ms * 1e-3 + st["ms_norm"] * 1e-3) / 1e9
         atom_time_ms = planes * touched / (red_peak * 1e9) * 1e3
         roofline = {"bound": "hbm", "achieved": alg_bytes / (dep_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (dep_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": pk_kind,
-                    "kernel": "deposit phase (k_gather2d + k_scatter2d)" if dims == 2 else "k_scatter3d",
+                    "kernel": {2: "deposit phase (k_gather2d + k_scatter2d)", 3: "k_scatter3d", 0: "k_healpix"}[dims],
                     "note": "FP64-issue bound, not HBM bound: see fp64/atomic roofs (SURVEY.md §8d)",
                     "fp64": {"achieved_gflops": fp64_ach, "peak_gflops": fp64_peak, "frac": fp64_ach / fp64_peak,
                              "flop_per_footprint_pixel": flop_per_px, "footprint_pixels": fpx,
@@ -325,7 +353,7 @@ def main():
                     "atomic": {"reds": planes * touched, "peak_gred_s": red_peak, "t_atomic_ms": atom_time_ms,
                                "frac_of_step": atom_time_ms / ms_step}}
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not healpix:
             from oracle import oracle as orc
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or (32768 if dims == 2 else 1 << 18)

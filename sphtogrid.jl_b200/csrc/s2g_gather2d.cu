@@ -23,8 +23,8 @@ namespace {
 constexpr int TILE_W = 64;     // tile width  (j, the contiguous image axis): 2 warps side by side
 constexpr int RPT = 8;         // rows per thread
 constexpr int TILE_H = 4 * RPT;  // tile height (i): 4 row groups of RPT rows -> 256 threads
-constexpr int BATCH = 128;     // particle records staged in shared memory at a time
-constexpr int CHUNK = 2048;    // max pairs per work item
+constexpr int BATCH = 256;     // particle records staged in shared memory at a time
+constexpr int CHUNK = 4096;    // max pairs per work item
 
 struct __align__(16) GRec {
     int iMin, iMax, jMin, jMax;  // footprint; iMin > iMax: record unused (particle re-routed to the scatter kernel)
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict_
 // of each chord of the kernel disc compared with 32-wide rows); warp w: column group w&3, row block w>>2;
 // thread rows: i = i0 + (w>>2)*2*RPT + 2*r + (lane>>4), r = 0..RPT-1.
 template <int KID>
-__global__ void __launch_bounds__(256, 2) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
+__global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
                                                      const unsigned* __restrict__ tile_beg,
                                                      const unsigned* __restrict__ tile_end,
                                                      const unsigned* __restrict__ chunk_begin,  // ntiles+1
@@ -508,7 +508,7 @@ int launch_gather(s2g_ctx* ctx, const GRec* recs, const unsigned* vals, const un
                   const s2g_particles& P, const s2g_geom& G, int image_k, double* image)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * 2);
+    const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * 3);
     k_gather2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles, ntile_j,
                                                             total_chunks, P.binq, P.in_dtype, G.n_images, image_k,
                                                             G.npix, image, ctx->d_counters);

@@ -1,0 +1,188 @@
+# SPHtoGridCUDA.jl — the reference-side binding of libsphtogrid_cuda.so.
+#
+# This is the file a SPHtoGrid.jl maintainer would `include` (after the existing includes in src/SPHtoGrid.jl) to
+# swap the bodies of the deposit hot path for calls into the B200 library.  It re-defines, with IDENTICAL signatures,
+#
+#   cic_mapping_2D            (src/cic_interpolation/cic_2D.jl:103-111)
+#   cic_mapping_3D            (src/cic_interpolation/cic_3D.jl:110-115)
+#   reduce_image_2D / _3D     (src/cic_interpolation/reduce_image.jl:8-10, :39-40)
+#   the particle loop of healpix_map (src/healpix_interpolation/main.jl:143-213) as `healpix_deposit!`
+#
+# so that `sphMapping`, `map_it`, `healpix_map`, `distributed_cic_map` ... keep working unchanged on top of them.
+# Julia is not installed in the build environment of this repository, so this file has not been executed here;
+# it is a mechanical transcription of the ctypes binding in ../_lib.py, which IS exercised by the test-suite.
+#
+# Memory layout notes: Julia `Matrix{T}(3,N)` positions, `Vector{T}(N)` fields and `Matrix{Float64}(Npix, Nimg+1)`
+# images are passed as-is (column-major = what the C ABI documents); nothing is copied on the Julia side.
+
+module SPHtoGridCUDA
+
+using SPHKernels
+
+const LIB = get(ENV, "SPHTOGRID_CUDA_LIB", "libsphtogrid_cuda")
+
+const S2G_F32 = Int32(0)
+const S2G_F64 = Int32(1)
+
+struct S2GStats
+    n_in::Int64; n_mapped::Int64; footprint_pixels::Int64; touched_pixels::Int64; n_fallback::Int64
+    n_pairs::Int64; n_scatter::Int64; n_gather::Int64; n_launches::Int64
+    ms_h2d::Float64; ms_compute::Float64; ms_d2h::Float64; ms_total::Float64
+    ms_prep::Float64; ms_sort::Float64; ms_norm::Float64; ms_deposit::Float64; ms_epilogue::Float64
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:s2g_init, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h))
+        ctx = new(h[])
+        finalizer(c -> ccall((:s2g_shutdown, LIB), Cint, (Ptr{Cvoid},), c.handle), ctx)
+        return ctx
+    end
+end
+
+const _default_ctx = Ref{Union{Nothing,Context}}(nothing)
+default_context() = something(_default_ctx[], (_default_ctx[] = Context(0)))
+
+last_error() = unsafe_string(ccall((:s2g_last_error, LIB), Cstring, ()))
+check(rc::Integer) = rc == 0 ? nothing : error("libsphtogrid_cuda ($rc): " * last_error())
+
+kernel_id(::Cubic) = Int32(0)
+kernel_id(::Quintic) = Int32(1)
+kernel_id(::WendlandC2) = Int32(2)
+kernel_id(::WendlandC4) = Int32(3)
+kernel_id(::WendlandC6) = Int32(4)
+kernel_id(::WendlandC8) = Int32(5)
+
+# all six particle arrays must share one element type across the ABI; promotion to Float64 is exact
+function _uniform(Pos, HSML, M, Rho, Bin_Q, Weights)
+    T = (eltype(Pos) == Float32 && all(a -> eltype(a) == Float32, (HSML, M, Rho, Bin_Q, Weights))) ? Float32 : Float64
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    return T, conv(Pos), conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+end
+
+"""
+    cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=nothing; param, kernel, show_progress, calc_mean, stokes)
+
+Drop-in for src/cic_interpolation/cic_2D.jl:103-244.  Returns `Matrix{Float64}(Nx*Ny, N_images+1)`.
+"""
+function cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=nothing;
+                        param, kernel::AbstractSPHKernel, show_progress::Bool=false,
+                        calc_mean::Bool=true, stokes::Bool=false, ctx::Context=default_context())
+    (!isnothing(RM) || stokes) && error("RM / stokes mapping is not supported by libsphtogrid_cuda (S2G_EUNSUPPORTED)")
+    T, pos, hsml, m, rho, bq, w = _uniform(Pos, HSML, M, Rho, Bin_Q, Weights)
+    N = length(m)
+    n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
+    nx, ny = param.Npixels[1], param.Npixels[2]
+    image = Matrix{Float64}(undef, nx * ny, n_images + 1)
+    GC.@preserve pos hsml m rho bq w image begin
+        check(ccall((:s2g_deposit_2d, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Int32, Float64, Int64, Int64, Int32, Int32, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, pos, hsml, m, rho, bq, w, N, n_images, T == Float32 ? S2G_F32 : S2G_F64,
+                    Float64(param.len2pix), nx, ny, kernel_id(kernel), calc_mean, image, C_NULL))
+    end
+    return image
+end
+
+"""
+    cic_mapping_3D(Pos, HSML, M, Rho, Bin_Q, Weights; param, kernel, show_progress, calc_mean)
+
+Drop-in for src/cic_interpolation/cic_3D.jl:110-209.  Returns `Matrix{Float64}(N^3, 2)`.
+"""
+function cic_mapping_3D(Pos, HSML, M, Rho, Bin_Q, Weights;
+                        param, kernel::AbstractSPHKernel, show_progress::Bool=false, calc_mean=false,
+                        ctx::Context=default_context())
+    T, pos, hsml, m, rho, bq, w = _uniform(Pos, HSML, M, Rho, Bin_Q, Weights)
+    N = length(m)
+    n = param.Npixels[1]
+    image = Matrix{Float64}(undef, n^3, 2)
+    GC.@preserve pos hsml m rho bq w image begin
+        check(ccall((:s2g_deposit_3d, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Float64, Int64, Int32, Int32, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, pos, hsml, m, rho, bq, w, N, T == Float32 ? S2G_F32 : S2G_F64,
+                    Float64(param.len2pix), n, kernel_id(kernel), calc_mean, image, C_NULL))
+    end
+    return image
+end
+
+"reduce_image.jl:8-31"
+function reduce_image_2D(image::Matrix{<:Real}, x_pixels::Int64, y_pixels::Int64, reduce_image::Bool;
+                         ctx::Context=default_context())
+    img = convert(Matrix{Float64}, image)
+    n_images = size(img, 2) - 1
+    out = Array{Float64,3}(undef, y_pixels, x_pixels, n_images)
+    GC.@preserve img out check(ccall((:s2g_reduce_image_2d, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int32, Int32, Ptr{Float64}),
+        ctx.handle, img, x_pixels, y_pixels, n_images, reduce_image, out))
+    return out
+end
+
+"reduce_image.jl:39-55 (the caller has already set image[:,2] .= 1 when !reduce_image, so reduce_image=true here)"
+function reduce_image_3D(image::Matrix{<:Real}, x_pixels::Int64, y_pixels::Int64, z_pixels::Int64;
+                         ctx::Context=default_context())
+    img = convert(Matrix{Float64}, image)
+    out = Array{Float64,3}(undef, z_pixels, y_pixels, x_pixels)
+    GC.@preserve img out check(ccall((:s2g_reduce_image_3d, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}),
+        ctx.handle, img, x_pixels, Int32(1), out))
+    return out
+end
+
+"""
+    healpix_deposit!(allsky_map, weight_map, pos, hsml, m, rho, bin_q, weights, Nside, kernel, calc_mean)
+
+Replaces the `for ipart ∈ 1:Npart` loop of healpix_map (src/healpix_interpolation/main.jl:143-213); the two
+`HealpixMap{Float64,RingOrder}` are filled through their `.pixels` vectors.
+"""
+function healpix_deposit!(allsky_map, weight_map, pos::Matrix{Float64}, hsml::Vector{Float64}, m::Vector{Float64},
+                          rho::Vector{Float64}, bin_q::Vector{Float64}, weights::Vector{Float64},
+                          Nside::Integer, kernel::AbstractSPHKernel, calc_mean::Bool;
+                          ctx::Context=default_context())
+    a, w = allsky_map.pixels, weight_map.pixels
+    GC.@preserve pos hsml m rho bin_q weights a w begin
+        check(ccall((:s2g_healpix_deposit, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, pos, hsml, m, rho, bin_q, weights, length(hsml), S2G_F64, Nside,
+                    kernel_id(kernel), calc_mean, a, w, C_NULL))
+    end
+    return allsky_map, weight_map
+end
+
+"""
+    sphmap_fused(Pos, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions, calc_mean,
+                 reduce_image, return_both_maps)
+
+The whole body of `sphMapping` (centre -> filter -> deposit -> reduce) in ONE call (s2g_sphmap); `Pos` is
+recentred in place exactly like center_particles does (src/cic_interpolation/filter_shift.jl:15).
+"""
+function sphmap_fused(Pos::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions::Int=2,
+                      calc_mean::Bool=false, reduce_image::Bool=true, return_both_maps::Bool=false,
+                      ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+    N = length(m)
+    n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
+    n = par_centred.Npixels[1]
+    out = dimensions == 2 ? (return_both_maps ? Matrix{Float64}(undef, n * n, n_images + 1) :
+                                                Array{Float64,3}(undef, n, n, n_images)) :
+                            Array{Float64,3}(undef, n, n, n)
+    shift = Float64.(param.center); half = Float64.(par_centred.halfsize)
+    pos_out = similar(Pos)
+    GC.@preserve Pos hsml m rho bq w out shift half pos_out begin
+        check(ccall((:s2g_sphmap, LIB), Cint,
+                    (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Float64, Int64, Int32, Int32,
+                     Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, dimensions, Pos, hsml, m, rho, bq, w, N, n_images, T == Float32 ? S2G_F32 : S2G_F64,
+                    shift, param.periodic, Float64(param.boxsize), half, Float64(par_centred.len2pix), n,
+                    kernel_id(kernel), calc_mean, reduce_image, return_both_maps, pos_out, out, C_NULL))
+    end
+    Pos .= pos_out
+    return out
+end
+
+end # module
