@@ -101,26 +101,29 @@ __device__ __forceinline__ long long hp_ang2pix_ring(const HpGeom& g, double the
 // colatitude-dependent part of pix2ang_ring for a whole ring: theta = acos(z_ring), returns sin/cos(theta) and the
 // azimuth step so that phi(j) = (j + 1 - off) * kPi / den  for the 0-based in-ring index j
 struct RingTrig {
-    double st, ct, off, den;
+    double st, ct, off, inv_den;
 };
 __device__ __forceinline__ RingTrig hp_ring_trig(const HpGeom& g, long long ring)
 {
     RingTrig t;
-    double theta;
+    double z, den;
     if (ring < g.nside) {
-        theta = acos(__dadd_rn(1.0, -__ddiv_rn((double)(ring * ring), g.fact2_p2a)));
-        t.off = 0.5; t.den = __dmul_rn(2.0, (double)ring);
+        z = __dadd_rn(1.0, -__ddiv_rn((double)(ring * ring), g.fact2_p2a));
+        t.off = 0.5; den = __dmul_rn(2.0, (double)ring);
     } else if (ring <= 3 * g.nside) {
-        theta = acos(__ddiv_rn((double)(g.nl2 - ring), g.fact1_p2a));
+        z = __ddiv_rn((double)(g.nl2 - ring), g.fact1_p2a);
         t.off = 0.5 * (double)(1 + ((ring + g.nside) & 1));
-        t.den = __dmul_rn(2.0, (double)g.nside);
+        den = __dmul_rn(2.0, (double)g.nside);
     } else {
         const long long rs = g.nl4 - ring;
-        theta = acos(__dadd_rn(-1.0, __ddiv_rn((double)(rs * rs), g.fact2_p2a)));
-        t.off = 0.5; t.den = __dmul_rn(2.0, (double)rs);
+        z = __dadd_rn(-1.0, __ddiv_rn((double)(rs * rs), g.fact2_p2a));
+        t.off = 0.5; den = __dmul_rn(2.0, (double)rs);
     }
-    t.st = sin(theta);
-    t.ct = cos(theta);
+    // pix2vecRing = (sinθ cosφ, sinθ sinφ, cosθ) with θ = acos(z): cosθ = z and sinθ = sqrt((1-z)(1+z)) without the
+    // round trip through acos (differs from sin(acos(z)) by a few ulp; see DESIGN.md "HEALPix conditioning")
+    t.ct = z;
+    t.st = sqrt((1.0 - z) * (1.0 + z));
+    t.inv_den = 1.0 / den;
     return t;
 }
 
@@ -134,6 +137,9 @@ struct Disc {
     long long irmin, irmax;               // disc rings (others are full cap rings)
     long long cpix;                       // pixel containing the centre (ang2pix)
     bool full_sky;
+    double ux, uy, uz;            // unit vector to the particle
+    double inv_ang, inv_aD2;      // 1/ang_pix, 1/(ang_pix*Dx)^2
+    bool small;                   // disc (+ one pixel) below 0.2 rad: asin by its series
 };
 
 __device__ __forceinline__ void make_disc(const HpGeom& g, Disc& d)
@@ -189,24 +195,35 @@ __device__ __forceinline__ void ring_run(const HpGeom& g, const Disc& d, long lo
     cnt = c;
 }
 
-// weight_per_index (pixel_weights.jl:34-76) for the pixel at in-ring index j of a ring with trig constants rt
+// weight_per_index (pixel_weights.jl:34-76) for the pixel at in-ring index j of a ring with trig constants rt.
+// The angular distance to the pixel centre is evaluated from the CHORD between the two unit vectors,
+// dx = 2 asin(|p̂ - ĉ| / 2), instead of the reference's acos(min(p·c/Δx, 1)): same angle, but well conditioned at the
+// sub-degree separations that matter here (acos loses ε/dx² relative accuracy) and without a division or acos call.
 template <int KID>
 __device__ __forceinline__ void pixel_weight(const HpGeom& g, const Disc& d, const RingTrig& rt, long long j, double& A,
                                              double& wk, bool& inside)
 {
-    const double phi = __ddiv_rn(__dmul_rn(__dadd_rn((double)(j + 1), -rt.off), kPi), rt.den);
     double sp, cp;
-    sincos(phi, &sp, &cp);
-    const double cx = __dmul_rn(rt.st, cp), cy = __dmul_rn(rt.st, sp), cz = rt.ct;
-    // distance_to_pixel_center (pixel_weights.jl:16-22): d accumulates from 0.0, one rounded product at a time
-    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d.px, cx), __dmul_rn(d.py, cy)), __dmul_rn(d.pz, cz));
-    const double t = __ddiv_rn(dot, d.Dx);
-    const double dx = acos(fmin(t, 1.0));
-    const double u = __dmul_rn(dx, d.hinv);
+    sincospi(((double)(j + 1) - rt.off) * rt.inv_den, &sp, &cp);  // phi = (iphi - off) * pi / den
+    const double ex = fma(rt.st, cp, -d.ux), ey = fma(rt.st, sp, -d.uy), ez = rt.ct - d.uz;
+    const double c2 = fma(ex, ex, fma(ey, ey, ez * ez));
+    const double hc = 0.5 * sqrt(c2);  // half chord = sin(dx/2)
+    double dx;
+    if (d.small) {
+        const double x2 = hc * hc;
+        double pser = fma(x2, 135135.0 / 9676800.0, 10395.0 / 599040.0);
+        pser = fma(pser, x2, 945.0 / 42240.0);
+        pser = fma(pser, x2, 105.0 / 3456.0);
+        pser = fma(pser, x2, 15.0 / 336.0);
+        pser = fma(pser, x2, 3.0 / 40.0);
+        pser = fma(pser, x2, 1.0 / 6.0);
+        dx = 2.0 * fma(hc * x2, pser, hc);
+    } else
+        dx = 2.0 * asin(fmin(hc, 1.0));
+    const double u = dx * d.hinv;
     // contributing_area (pixel_weights.jl:6-8) then / (ang_pix*Dx)^2 (:53)
-    const double inner = fabs(__dadd_rn(d.proj_h, -__dadd_rn(dx, -__dmul_rn(0.5, g.ang_pix))));
-    const double aD = __dmul_rn(g.ang_pix, d.Dx);
-    A = __ddiv_rn(__ddiv_rn(fmax(0.0, fmin(g.ang_pix, inner)), g.ang_pix), __dmul_rn(aD, aD));
+    const double inner = fabs(d.proj_h - (dx - 0.5 * g.ang_pix));
+    A = fmax(0.0, fmin(g.ang_pix, inner)) * d.inv_ang * d.inv_aD2;
     inside = (u <= 1.0);
     wk = inside ? kernel_shape<KID>(u) : 0.0;
 }
@@ -233,6 +250,13 @@ __global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int 
         d.proj_h = asin(__ddiv_rn(hs, d.Dx));
         d.hinv = __ddiv_rn(1.0, d.proj_h);
         make_disc(g, d);
+        d.ux = d.px / d.Dx; d.uy = d.py / d.Dx; d.uz = d.pz / d.Dx;
+        d.inv_ang = 1.0 / g.ang_pix;
+        {
+            const double aD0 = g.ang_pix * d.Dx;
+            d.inv_aD2 = 1.0 / (aD0 * aD0);
+        }
+        d.small = (d.proj_h + 2.0 * g.ang_pix) < 0.2;
 
         // ---- pass A
         double sw = 0.0, sa = 0.0;

@@ -122,8 +122,11 @@ def test_healpix_deposit_parity_all_regimes(s2g, oracle, nside):
         for k in ("n_mapped", "n_fallback", "touched_pixels"):
             assert st[k] == ost[k], k
         assert st["n_fallback"] > 0
-        assert_parity(wm, rw, rtol=5e-9, what=f"healpix weight map nside={nside}")
-        assert_parity(a, ra, rtol=5e-9, what=f"healpix map nside={nside}")
+        # the reference formula acos(p.c/r) itself carries a rounding error of ~eps/dx^2 (1e-8 at the pixel scale of
+        # Nside 256); the GPU evaluates the same angle from the chord (well conditioned), so beyond that level the
+        # comparison measures the oracle's acos, not the GPU
+        assert_parity(wm, rw, rtol=5e-8, what=f"healpix weight map nside={nside}")
+        assert_parity(a, ra, rtol=5e-8, what=f"healpix map nside={nside}")
         assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12) and math.isclose(a.sum(), ra.sum(), rel_tol=1e-12)
 
 
