@@ -114,3 +114,65 @@ class StreamingAccumulator:
 
     def result_over_ranks(self):
         return combine_partial_images(self.sum)
+
+
+def _my_jobs(n_subfiles: int):
+    """Sub-snapshot files of this rank: the reference's dynamic job queue (distributed_mapping/main.jl:10-26) hands
+    job ids 0..n-1 to whichever worker is free; with one rank per GPU a round-robin split is the static equivalent."""
+    ws, rank = world()
+    return range(rank, n_subfiles, ws)
+
+
+def distributed_cic_map(cic_filename, Nsubfiles, mapping_function, param, Nimages=1, *, reduce_image=True, Ndim=2,
+                        snap=0, units="", vtk=True, write=True):
+    """Mirror of distributed_cic_map (src/distributed_mapping/cic.jl:24-110): one map per sub-snapshot file
+    (`mapping_function(subfile) -> (map(s), weight_map)`, e.g. the two parts of
+    `sphMapping(...; return_both_maps=true)`), summed with the reference's NaN/Inf guard, reduced once, saved.
+    Ranks split the files; the partial sums are combined with one all-reduce.  Returns the reduced image."""
+    from .mapping import reduce_image_2D, reduce_image_3D
+    n = int(param.Npixels[0])
+    n_distr = n ** Ndim
+    acc_map = StreamingAccumulator(n_distr * Nimages)
+    acc_w = StreamingAccumulator(n_distr)
+    for job in _my_jobs(Nsubfiles):
+        res = mapping_function(job)
+        if res is None or res[0] is None:
+            continue
+        local_map, local_weight = res
+        acc_map.add(local_map)
+        acc_w.add(local_weight)
+    sum_map = acc_map.result_over_ranks().reshape((n_distr, Nimages), order="F")
+    sum_w = acc_w.result_over_ranks()
+    flat = np.asfortranarray(np.concatenate([sum_map, sum_w[:, None]], axis=1))
+    if Ndim == 2:
+        image = reduce_image_2D(flat, n, n, reduce_image)
+    elif Ndim == 3:
+        image = reduce_image_3D(flat, n, n, n, True)  # the reference always divides in 3D (cic.jl:87)
+    else:
+        raise ValueError("Only 2D and 3D are possible")
+    if write and world()[1] == 0:
+        if Ndim == 3 and vtk:
+            np.save(cic_filename + ".npy", image)  # VTK output is outside this path (SURVEY.md §8 f2)
+        else:
+            from .io import write_fits_image
+            write_fits_image(cic_filename, image, param, snap=snap, units=units)
+    return image
+
+
+def distributed_allsky_map(allsky_filename, Nside, Nsubfiles, mapping_function, *, reduce_image=True, write=False):
+    """Mirror of distributed_allsky_map (src/distributed_mapping/healpix.jl:16-87).  `mapping_function(subfile)` returns
+    `(allsky_map, weight_map)` of `healpix_map`.  Returns `(sum_allsky, sum_weights)` (the first divided by the second
+    where the weight is finite and non-zero when reduce_image)."""
+    npix = 12 * int(Nside) ** 2
+    acc_a, acc_w = StreamingAccumulator(npix), StreamingAccumulator(npix)
+    for job in _my_jobs(Nsubfiles):
+        a, w = mapping_function(job)
+        acc_a.add(a)
+        acc_w.add(w)
+    sum_a, sum_w = acc_a.result_over_ranks(), acc_w.result_over_ranks()
+    if reduce_image:
+        ok = np.isfinite(sum_w) & (sum_w != 0)
+        sum_a[ok] /= sum_w[ok]
+    if write and world()[1] == 0:
+        np.save(allsky_filename + ".npy", sum_a)  # HEALPix FITS tables are outside this path (SURVEY.md §8 f2)
+    return sum_a, sum_w
