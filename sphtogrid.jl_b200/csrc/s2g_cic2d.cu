@@ -71,6 +71,7 @@ __device__ __forceinline__ void warp_deposit_2d(const Rec2& r, const s2g_particl
     }
     const double kernel_norm = r.area / n_distr;
     const double area_norm = kernel_norm * wpp * r.w * r.dz;
+    const bool poison = !isfinite(area_norm);
 
     // ---- pass B: pix_weight = wk·A·area_norm; update_image! (cic_shared.jl:111-121)
     const long long npl = G.npix * G.npix;
@@ -91,8 +92,13 @@ __device__ __forceinline__ void warp_deposit_2d(const Rec2& r, const s2g_particl
                 wk = 1.0;
             else {
                 const double u = u_of(__dmul_rn(xd, xd), yd2, r.hinv);
-                if (!(u <= 1.0)) continue;
-                wk = kernel_shape<KID>(u);
+                if (!(u <= 1.0)) {
+                    // wk = 0: pix_weight = 0*A*area_norm is 0 and skipped — unless area_norm is Inf/NaN (rho = 0,
+                    // NaN weights): then the reference's `!iszero(pix_weight)` is true for the whole bounding box
+                    if (!poison) continue;
+                    wk = 0.0;
+                } else
+                    wk = kernel_shape<KID>(u);
             }
             const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
             const double pw = wk * (dx * dy) * area_norm;

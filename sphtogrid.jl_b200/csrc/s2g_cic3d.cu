@@ -109,6 +109,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     }
     const double kernel_norm = r.vol / n_distr;                       // cic_3D.jl:168
     const double volume_norm = kernel_norm * wpp * r.w * G.len2pix;   // :169
+    const bool poison = !isfinite(volume_norm);
 
     const long long n = G.npix, npl = n * n * n;
     for (int kc = c0; kc < nk; kc += W) {
@@ -130,8 +131,11 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                 else {
                     const double s = __dadd_rn(__dadd_rn(__dmul_rn(xd, xd), yd2), zd2);
                     const double u = __dmul_rn(__dsqrt_rn(s), r.hinv);
-                    if (!(u <= 1.0)) continue;
-                    wk = kernel_shape<KID>(u);
+                    if (!(u <= 1.0)) {
+                        if (!poison) continue;  // see s2g_cic2d.cu: Inf/NaN norm marks the whole bounding box
+                        wk = 0.0;
+                    } else
+                        wk = kernel_shape<KID>(u);
                 }
                 const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
                 const double pw = wk * (dx * dy * dz) * volume_norm;

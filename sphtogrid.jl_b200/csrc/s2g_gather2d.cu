@@ -258,8 +258,9 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
         g.iMin = r.iMin; g.iMax = r.iMax; g.jMin = r.jMin; g.jMax = r.jMax;
         g.p = (int)p; g.pad = 0;
         unsigned np = 0;
-        if (sw == 0.0) {
-            // cic_2D.jl:51-66 branch -> scatter kernel
+        const double an_probe = (r.area / sw) * r.w * r.dz;
+        if (sw == 0.0 || !isfinite(an_probe)) {
+            // cic_2D.jl:51-66 branch, or an Inf/NaN normalisation (rho = 0, NaN weight) -> scatter kernel
             g.iMin = 1; g.iMax = 0; g.an = 0.0;
             if (lane == 0) reroute[atomicAdd(&counters[CNT_PAIRS], 1ull)] = (int)p;
         } else {

@@ -254,3 +254,24 @@ def test_distributed_cic_map_subfile_streaming(s2g, oracle, tmp_path):
     assert_parity(image[mask], whole[mask], rtol=1e-12, what="distributed_cic_map vs single map")
     d, par2, snap, units = s2g.read_fits_image(fn)
     assert np.array_equal(d, image[:, :, 0]) and snap == 7 and units == "K"
+
+
+@pytest.mark.parametrize("strategy", ["scatter", "gather"])
+def test_non_finite_normalisation_marks_bounding_box(s2g, oracle, strategy):
+    """rho = 0 (dz = Inf) or a NaN weight make pix_weight = wk*A*area_norm Inf inside the kernel and 0*Inf = NaN outside:
+    the reference's `!iszero(pix_weight)` then updates the whole bounding box.  Zero weight deposits nothing."""
+    pos, hsml, m, rho, q, w = random_particles(71, 400, box=9.0, hmin=0.2, hmax=1.5)
+    rho[3] = 0.0
+    w[10] = np.nan
+    w[20] = 0.0
+    m[30] = 0.0
+    npix = 96
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=npix)
+    ctx = s2g.Context(0, strategy=strategy)
+    got = s2g.cic_mapping_2D(pos, hsml, m, rho, q, w, param=par, kernel=s2g.WendlandC4(2), calc_mean=True, ctx=ctx)
+    ref, _ = oracle.cic_mapping_2d(pos, hsml, m, rho, q, w, par.len2pix, npix, "WendlandC4", 2, True)
+    assert np.isnan(ref).any() and np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert_parity(np.where(fin, got, 0.0), np.where(fin, ref, 0.0), what="finite part")
+    ctx.close()
