@@ -35,6 +35,8 @@ WORKLOADS = {
                desc="synthetic 128M particles, healpix_map all-sky Nside=2048, WendlandC4, shell [0.05L,0.5L]"),
     "c4s": dict(n=4 * 1024 * 1024, npix=2048, dims=0, kernel="WendlandC4", n_ngb=200.0, seed=4,
                 desc="4M particles of the c4 stream (hsml of the 128M set), Nside=2048 (debug)", n_stream=128 * 1024 * 1024),
+    "c4t": dict(n=256 * 1024, npix=2048, dims=0, kernel="WendlandC4", n_ngb=200.0, seed=4,
+                desc="256k particles of the c4 stream, Nside=2048 (profiling)", n_stream=128 * 1024 * 1024),
     "c3s": dict(n=8 * 1024 * 1024, npix=512, dims=3, kernel="Cubic", n_ngb=64.0, seed=3,
                 desc="8M particles of the c3 stream, 512^3 (debug)", n_stream=64 * 1024 * 1024),
     "c5": dict(n=1024 * 1024 * 1024, npix=8192, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=5,

@@ -228,12 +228,237 @@ __device__ __forceinline__ void pixel_weight(const HpGeom& g, const Disc& d, con
     wk = inside ? kernel_shape<KID>(u) : 0.0;
 }
 
-template <int KID>
-__global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int calc_mean, double* __restrict__ amap,
-                                                 double* __restrict__ wmap, unsigned long long* __restrict__ counters)
+// ---- fast ring walk ---------------------------------------------------------------------------------------
+// polynomial coefficients live in the constant bank so that they are FP64-instruction operands (c[bank][off]) instead of
+// being re-materialised with UMOV/IMAD.MOV pairs inside the pixel loop
+__constant__ double kAsinC[7] = {1.0 / 6.0, 3.0 / 40.0, 15.0 / 336.0, 105.0 / 3456.0, 945.0 / 42240.0,
+                                 10395.0 / 599040.0, 135135.0 / 9676800.0};
+__constant__ double kRsq[2] = {0.375, 0.5};
+__constant__ double kWC4[3] = {56.0 / 3.0, -88.0 / 3.0, 35.0 / 3.0};
+__constant__ double kWC6[4] = {66.0, -154.0, 121.0, -32.0};
+// 1/sqrt(s), s > 0, ~2 ulp (MUFU.RSQ64H seed + one third-order Newton step)
+__device__ __forceinline__ double hp_rsqrt(double s)
 {
-    const int lane = threadIdx.x & 31;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double e = fma(-s, y * y, 1.0);
+    return fma(fma(e, kRsq[0], kRsq[1]), e * y, y);
+}
+
+// kernel shape from t = 1 - u, 0 < t <= 1 (no range test)
+template <int KID>
+__device__ __forceinline__ double hp_shape_t(double t)
+{
+    if (KID == S2G_KERNEL_CUBIC) {
+        const double a = fma(fma(fma(-6.0, t, 12.0), t, -6.0), t, 1.0), b = 2.0 * (t * t * t);
+        return t > 0.5 ? a : b;
+    } else if (KID == S2G_KERNEL_QUINTIC) {
+        const double b0 = t - 1.0 / 3.0, c0 = t - 2.0 / 3.0;
+        const double b = b0 > 0.0 ? b0 : 0.0, c = c0 > 0.0 ? c0 : 0.0;
+        const double a2 = t * t, b2 = b * b, c2 = c * c;
+        return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a2 * a2 * t));
+    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
+        const double t2 = t * t;
+        return (t2 * t2) * fma(-4.0, t, 5.0);
+    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
+        const double t2 = t * t;
+        return (t2 * t2 * t2) * fma(fma(kWC4[2], t, kWC4[1]), t, kWC4[0]);
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        const double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4) * fma(fma(fma(kWC6[3], t, kWC6[2]), t, kWC6[1]), t, kWC6[0]);
+    } else {
+        const double t2 = t * t, t4 = t2 * t2, u = 1.0 - t;
+        return (t4 * t4 * t2) * fma(fma(fma(fma(429.0, u, 450.0), u, 210.0), u, 50.0), u, 5.0);
+    }
+}
+
+// per-particle constants of the fast path
+struct DiscFast {
+    double ux, uy, uz, hinv, proj_h, half_ang, ang, a_scale;  // a_scale = 1/(ang_pix * (ang_pix*Dx)^2)
+    double cl, sl, belt_inv_den;  // rotation by `lane` pixels of an equatorial-belt ring (all belt rings share Δφ)
+    bool small;
+};
+
+// A (contributing area / (ang_pix Dx)^2) and kernel weight of the pixel whose centre is (st*cp, st*sp, ct)
+template <int KID>
+__device__ __forceinline__ void hp_pixel(const DiscFast& f, double st, double ez2, double cp, double sp, double& A,
+                                         double& wk, bool& inside)
+{
+    const double ex = fma(st, cp, -f.ux), ey = fma(st, sp, -f.uy);
+    const double c2 = fma(ex, ex, fma(ey, ey, ez2)) + 1e-300;  // squared chord between the unit vectors (> 0)
+    const double hc = 0.5 * (c2 * hp_rsqrt(c2));                    // sin(dx/2)
+    double dx;
+    if (f.small) {  // asin series, |hc| <= 0.1
+        const double x2 = 0.25 * c2;
+        double ps = fma(x2, kAsinC[6], kAsinC[5]);
+        ps = fma(ps, x2, kAsinC[4]);
+        ps = fma(ps, x2, kAsinC[3]);
+        ps = fma(ps, x2, kAsinC[2]);
+        ps = fma(ps, x2, kAsinC[1]);
+        ps = fma(ps, x2, kAsinC[0]);
+        dx = 2.0 * fma(hc * x2, ps, hc);
+    } else
+        dx = 2.0 * asin(hc < 1.0 ? hc : 1.0);
+    const double t = fma(-dx, f.hinv, 1.0);  // 1 - u
+    inside = (t >= 0.0);
+    const double inner = fabs(f.proj_h - (dx - f.half_ang));  // >= 0: max(0, min(ang, inner)) = min(ang, inner)
+    A = (inner < f.ang ? inner : f.ang) * f.a_scale;
+    const double w0 = hp_shape_t<KID>(t);
+    wk = (t > 0.0) ? w0 : 0.0;
+}
+
+// walk the run [j0, j0+cnt) (mod nr) of one ring with the lanes along the ring; azimuth by exact sincospi for each
+// lane's first pixel and by rotation through 32 pixel steps afterwards (re-seeded exactly every 8 steps)
+template <int KID, bool PASS_B>
+__device__ __forceinline__ void hp_walk_ring(const DiscFast& f, const RingTrig& rt, double c0, double s0, double c32,
+                                             double s32, int sp, int nr, int j0, int cnt, int lane, int cpix,
+                                             double area_norm, bool fb, double q, bool q_finite,
+                                             double* __restrict__ amap, double* __restrict__ wmap, double& sw,
+                                             double& sa, long long& n_in, bool& found_c)
+{
+    const double ez = rt.ct - f.uz, ez2 = ez * ez;
+    const bool belt = (rt.inv_den == f.belt_inv_den);
+    int nin = 0;
+    for (int t0 = lane; t0 < cnt; t0 += 256) {  // exact azimuth every 8 steps of 32 pixels, rotation in between
+        int j = j0 + t0;
+        if (j >= nr) j -= nr;
+        double cp, sph;
+        if (belt && t0 < 32) {  // first pixel of the run rotated by `lane` pixels (belt rings share the pixel step)
+            cp = fma(c0, f.cl, -s0 * f.sl);
+            sph = fma(s0, f.cl, c0 * f.sl);
+        } else
+            sincospi(((double)(j + 1) - rt.off) * rt.inv_den, &sph, &cp);
+        const int tend = min(t0 + 256, cnt);
+        for (int t = t0; t < tend; t += 32) {
+            double A, wk;
+            bool inside;
+            hp_pixel<KID>(f, rt.st, ez2, cp, sph, A, wk, inside);
+            if (!PASS_B) {
+                sa += A;
+                sw = fma(wk, A, sw);  // wk = 0 outside
+                nin += inside ? 1 : 0;
+                found_c = found_c || (sp + j == cpix);
+            } else {
+                if (fb) wk = 1.0;
+                const double pw = area_norm * wk * A;
+                if (pw != 0.0 || !q_finite) {
+                    red_add(amap + sp + j, q * pw);
+                    red_add(wmap + sp + j, pw);
+                }
+            }
+            const double c_new = fma(cp, c32, -sph * s32), s_new = fma(sph, c32, cp * s32);
+            cp = c_new; sph = s_new;
+            j += 32;
+            if (j >= nr) j -= nr;
+        }
+    }
+    n_in += nin;
+}
+
+// per-warp staging of the set-up of up to 32 rings (one ring per lane), so that the expensive uniform part of the
+// disc walk (ring_above / atan2 / sqrt per ring) is computed ONCE per ring by one lane instead of by all 32
+struct RingBatch {
+    int sp[32], nr[32], j0[32], cnt[32], pre[33];
+    double st[32], ct[32], off[32], inv_den[32];
+    double c0[32], s0[32], c32[32], s32[32];  // azimuth of the run's first pixel; rotation by 32 pixels
+};
+
+template <int KID, bool PASS_B>
+__device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d, const DiscFast& f, RingBatch& rb,
+                                                 long long ring0, int nb, bool setup, int lane, double area_norm,
+                                                 bool fb, double q, bool q_finite, double* __restrict__ amap,
+                                                 double* __restrict__ wmap, double& sw, double& sa, long long& n_in,
+                                                 long long& n_tot, bool& found_c)
+{
+    if (setup) {
+        int cnt_l = 0;
+        if (lane < nb) {
+            const long long ring = ring0 + lane;
+            long long sp, nr, j0, cnt;
+            bool sh;
+            hp_ring_info(g, ring, sp, nr, sh);
+            ring_run(g, d, ring, nr, sh, j0, cnt);
+            const RingTrig rt = hp_ring_trig(g, ring);
+            rb.sp[lane] = (int)sp; rb.nr[lane] = (int)nr; rb.j0[lane] = (int)j0; rb.cnt[lane] = (int)cnt;
+            rb.st[lane] = rt.st; rb.ct[lane] = rt.ct; rb.off[lane] = rt.off; rb.inv_den[lane] = rt.inv_den;
+            double sa_, ca_;
+            sincospi(((double)(j0 + 1) - rt.off) * rt.inv_den, &sa_, &ca_);
+            rb.c0[lane] = ca_; rb.s0[lane] = sa_;
+            sincospi(32.0 * rt.inv_den, &sa_, &ca_);
+            rb.c32[lane] = ca_; rb.s32[lane] = sa_;
+            cnt_l = (int)cnt;
+        }
+        // exclusive prefix of the run lengths (flattened walk) and the batch total
+        int incl = cnt_l;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        rb.pre[lane] = incl - cnt_l;
+        if (lane == 31) rb.pre[32] = incl;
+        __syncwarp();
+    }
+    const int total = rb.pre[32];
+    if (!PASS_B) n_tot += total;
+    if (total == 0) return;
+    if (total >= 24 * nb) {
+        // long runs: ring by ring, lanes along the ring, azimuth by rotation
+        for (int r = 0; r < nb; ++r) {
+            const int cnt = rb.cnt[r];
+            if (cnt == 0) continue;
+            RingTrig rt;
+            rt.st = rb.st[r]; rt.ct = rb.ct[r]; rt.off = rb.off[r]; rt.inv_den = rb.inv_den[r];
+            hp_walk_ring<KID, PASS_B>(f, rt, rb.c0[r], rb.s0[r], rb.c32[r], rb.s32[r], rb.sp[r], rb.nr[r], rb.j0[r], cnt,
+                                      lane, (int)d.cpix, area_norm, fb, q, q_finite, amap, wmap, sw, sa, n_in, found_c);
+        }
+    } else {
+        // short runs: flatten (ring, pixel) over the lanes so that small discs still fill the warp
+        for (int t = lane; t < total; t += 32) {
+            int lo = 0, hi = nb;  // last ring with pre[ring] <= t
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                if (hi - lo > 1) { if (rb.pre[mid] <= t) lo = mid; else hi = mid; }
+            }
+            const int r = lo;
+            int j = rb.j0[r] + (t - rb.pre[r]);
+            if (j >= rb.nr[r]) j -= rb.nr[r];
+            double sp_, cp_;
+            sincospi(((double)(j + 1) - rb.off[r]) * rb.inv_den[r], &sp_, &cp_);
+            const double ez = rb.ct[r] - f.uz;
+            double A, wk;
+            bool inside;
+            hp_pixel<KID>(f, rb.st[r], ez * ez, cp_, sp_, A, wk, inside);
+            const long long pix = (long long)rb.sp[r] + j;
+            if (!PASS_B) {
+                sa += A;
+                if (inside) { sw = fma(wk, A, sw); ++n_in; }
+                if (pix == d.cpix) found_c = true;
+            } else {
+                if (fb) wk = 1.0;
+                const double pw = area_norm * wk * A;
+                if (pw != 0.0 || !q_finite) {
+                    red_add(amap + pix, q * pw);
+                    red_add(wmap + pix, pw);
+                }
+            }
+        }
+    }
+}
+
+template <int KID>
+__global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, int calc_mean,
+                                                    double* __restrict__ amap, double* __restrict__ wmap,
+                                                    unsigned long long* __restrict__ counters)
+{
+    __shared__ RingBatch s_rb[8];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    RingBatch& rb = s_rb[wq];
     unsigned long long touched = 0, fallback = 0, mapped = 0;
+    const double belt_inv_den = 1.0 / __dmul_rn(2.0, (double)g.nside);
+    double lane_c, lane_s;
+    sincospi((double)lane * belt_inv_den, &lane_s, &lane_c);
     for (;;) {
         long long p = 0;
         if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
@@ -257,39 +482,30 @@ __global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int 
             d.inv_aD2 = 1.0 / (aD0 * aD0);
         }
         d.small = (d.proj_h + 2.0 * g.ang_pix) < 0.2;
+        DiscFast f;
+        f.ux = d.ux; f.uy = d.uy; f.uz = d.uz; f.hinv = d.hinv; f.proj_h = d.proj_h;
+        f.half_ang = 0.5 * g.ang_pix; f.ang = g.ang_pix; f.a_scale = d.inv_ang * d.inv_aD2; f.small = d.small;
+        f.cl = lane_c; f.sl = lane_s; f.belt_inv_den = belt_inv_den;
+        const bool q_finite = isfinite(q);
+        const long long nrings = d.ring_last - d.ring_first + 1;
 
-        // ---- pass A
+        // ---- pass A (calculate_weights, pixel_weights.jl:87-140)
         double sw = 0.0, sa = 0.0;
         long long n_in = 0, n_tot = 0;
         bool found_c = false;
-        for (long long ring = d.ring_first; ring <= d.ring_last; ++ring) {
-            long long sp, nr, j0, cnt;
-            bool sh;
-            hp_ring_info(g, ring, sp, nr, sh);
-            ring_run(g, d, ring, nr, sh, j0, cnt);
-            if (cnt == 0) continue;
-            const RingTrig rt = hp_ring_trig(g, ring);
-            for (long long t = lane; t < cnt; t += 32) {
-                long long j = j0 + t;
-                if (j >= nr) j -= nr;
-                double A, wk;
-                bool inside;
-                pixel_weight<KID>(g, d, rt, j, A, wk, inside);
-                sa += A;
-                ++n_tot;
-                if (inside) { sw = fma(wk, A, sw); ++n_in; }
-                if (sp + j == d.cpix) found_c = true;
-            }
+        __syncwarp();
+        for (long long base = 0; base < nrings; base += 32) {
+            const int nb = (int)min(32LL, nrings - base);
+            hp_process_batch<KID, false>(g, d, f, rb, d.ring_first + base, nb, true, lane, 0.0, false, q, q_finite, amap,
+                                         wmap, sw, sa, n_in, n_tot, found_c);
+            if (base + 32 < nrings) __syncwarp();
         }
         found_c = __any_sync(0xffffffffu, found_c);
         // the centre pixel, when the disc walk did not visit it (push! + unique!)
-        long long c_ring = 0, c_j = 0;
-        RingTrig c_rt{};
         double cA = 0.0, cwk = 0.0;
         bool c_inside = false;
         if (!found_c) {
-            // ring of cpix
-            long long ring;
+            long long ring;  // ring of cpix
             if (d.cpix < g.ncap) {
                 ring = (long long)((1 + (long long)floor(sqrt((double)(1 + 2 * d.cpix)))) >> 1);
                 while (2 * ring * (ring - 1) > d.cpix) --ring;
@@ -306,19 +522,20 @@ __global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int 
             long long sp, nr;
             bool sh;
             hp_ring_info(g, ring, sp, nr, sh);
-            c_ring = ring; c_j = d.cpix - sp;
-            c_rt = hp_ring_trig(g, c_ring);
-            pixel_weight<KID>(g, d, c_rt, c_j, cA, cwk, c_inside);
+            const RingTrig c_rt = hp_ring_trig(g, ring);
+            double s_, c_;
+            sincospi(((double)(d.cpix - sp + 1) - c_rt.off) * c_rt.inv_den, &s_, &c_);
+            const double ez = c_rt.ct - f.uz;
+            hp_pixel<KID>(f, c_rt.st, ez * ez, c_, s_, cA, cwk, c_inside);
             if (lane == 0) {
                 sa += cA;
-                ++n_tot;
                 if (c_inside) { sw = fma(cwk, cA, sw); ++n_in; }
             }
+            ++n_tot;
         }
         sw = warp_sum(sw);
         sa = warp_sum(sa);
         n_in = warp_sum_ll(n_in);
-        n_tot = warp_sum_ll(n_tot);
 
         // ---- normalisation (pixel_weights.jl:119-137, main.jl:32-33, :188-193)
         bool fb = false;
@@ -338,42 +555,29 @@ __global__ void __launch_bounds__(256) k_healpix(s2g_particles P, HpGeom g, int 
         dz = __ddiv_rn(dz, __dmul_rn(aD, aD));
         const double kernel_norm = area / n_distr;
         const double area_norm = kernel_norm * wpp * ld_in(P.w, p, P.in_dtype) * dz;
-        const bool q_finite = isfinite(q);
 
-        // ---- pass B
-        for (long long ring = d.ring_first; ring <= d.ring_last; ++ring) {
-            long long sp, nr, j0, cnt;
-            bool sh;
-            hp_ring_info(g, ring, sp, nr, sh);
-            ring_run(g, d, ring, nr, sh, j0, cnt);
-            if (cnt == 0) continue;
-            const RingTrig rt = hp_ring_trig(g, ring);
-            for (long long t = lane; t < cnt; t += 32) {
-                long long j = j0 + t;
-                if (j >= nr) j -= nr;
-                double A, wk;
-                bool inside;
-                pixel_weight<KID>(g, d, rt, j, A, wk, inside);
-                if (fb) wk = 1.0;
-                const double pw = area_norm * wk * A;
-                if (pw != 0.0 || !q_finite) {
-                    red_add(amap + sp + j, q * pw);
-                    red_add(wmap + sp + j, pw);
-                }
-                ++touched;
+        // ---- pass B (update_image!, main.jl:25-45); a single batch is still staged in shared memory
+        {
+            double d0 = 0.0, d1 = 0.0;
+            long long l0 = 0, l1 = 0;
+            bool b0 = false;
+            for (long long base = 0; base < nrings; base += 32) {
+                const int nb = (int)min(32LL, nrings - base);
+                __syncwarp();
+                hp_process_batch<KID, true>(g, d, f, rb, d.ring_first + base, nb, nrings > 32, lane, area_norm, fb, q,
+                                            q_finite, amap, wmap, d0, d1, l0, l1, b0);
             }
         }
+        if (lane == 0) touched += (unsigned long long)n_tot;
         if (!found_c && lane == 0) {
             const double pw = area_norm * (fb ? 1.0 : cwk) * cA;
             if (pw != 0.0 || !q_finite) {
                 red_add(amap + d.cpix, q * pw);
                 red_add(wmap + d.cpix, pw);
             }
-            ++touched;
         }
         if (lane == 0) ++mapped;
     }
-    touched = (unsigned long long)warp_sum_ll((long long)touched);
     if (lane == 0) {
         if (touched) { atomicAdd(&counters[CNT_TOUCHED], touched); atomicAdd(&counters[CNT_FOOTPRINT], touched); }
         if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
