@@ -106,7 +106,7 @@ def reference_arm(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or (32768 if wl["dims"] == 2 else 1 << 18)
+    sample = args.cpu_sample or (131072 if wl["dims"] == 2 else 1 << 20)
     pos, hsml, m, rho, temp = host_particles(wl, sample)
     par = orc.mapping_parameters(center=[0.5, 0.5, 0.5], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=wl["npix"])
     times = []
@@ -358,7 +358,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not healpix:
             from oracle import oracle as orc
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample or (32768 if dims == 2 else 1 << 18)
+            sample = args.cpu_sample or (131072 if dims == 2 else 1 << 20)
             hp_, hh_, hm_, hr_, ht_ = host_particles(wl, sample)
             opar = orc.mapping_parameters(center=[0.5, 0.5, 0.5], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=npix)
             t0 = time.perf_counter()

@@ -37,7 +37,9 @@ __device__ __forceinline__ bool make_rec3(const s2g_particles& P, const s2g_geom
     return ok;
 }
 
-// lanes: W wide along k (contiguous axis, indices.jl:15-17), 32/W deep along j; i is looped by the whole warp
+// lanes: W wide along k (contiguous axis, indices.jl:15-17), 32/W deep along j; i is walked by the whole warp in groups
+// of four independent chains.  Coordinates in units of h: a cell centre is inside the kernel iff a²+b²+c² < 1
+// (the reference's u = sqrt(dx²+dy²+dz²)·h⁻¹ <= 1 up to the last ulp at the rim, where w -> 0 anyway).
 template <int KID>
 __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G, int lane,
                                                 double* __restrict__ image, unsigned long long& touched,
@@ -51,31 +53,42 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     const double dx_lo = overlap_1d(r.x, r.h, r.lo[0]), dx_hi = overlap_1d(r.x, r.h, r.hi[0]);
     const double dy_lo = overlap_1d(r.y, r.h, r.lo[1]), dy_hi = overlap_1d(r.y, r.h, r.hi[1]);
     const double dz_lo = overlap_1d(r.z, r.h, r.lo[2]), dz_hi = overlap_1d(r.z, r.h, r.hi[2]);
+    const double hinv = r.hinv;
+    const double xb = center_dist(r.x, (double)r.lo[0]) * hinv;  // a of the first i-plane
 
+    // ---- pass A (calculate_weights, cic_3D.jl:13-78)
     double sw = 0.0;
     int cnt = 0;
     for (int kc = c0; kc < nk; kc += W) {
         const int k = r.lo[2] + kc;
-        const double zd = center_dist(r.z, (double)k);
-        const double zd2 = __dmul_rn(zd, zd);
+        const double cz = center_dist(r.z, (double)k) * hinv;
         const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
         for (int jr = r0; jr < nj; jr += R) {
             const int j = r.lo[1] + jr;
-            const double yd = center_dist(r.y, (double)j);
-            const double yd2 = __dmul_rn(yd, yd);
+            const double by = center_dist(r.y, (double)j) * hinv;
+            const double bc2 = fma(by, by, cz * cz) + 1e-300;  // > 0 even when a cell centre sits on the particle
+            if (bc2 >= 1.0) continue;
             const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
-            for (int ii = 0; ii < ni; ++ii) {
-                const int i = r.lo[0] + ii;
-                const double xd = center_dist(r.x, (double)i);
-                // sqrt(dx*dx + dy*dy + dz*dz) * hinv, left to right (distances.jl:15-17)
-                const double s = __dadd_rn(__dadd_rn(__dmul_rn(xd, xd), yd2), zd2);
-                const double u = __dmul_rn(__dsqrt_rn(s), r.hinv);
-                if (u <= 1.0) {
+            double col = 0.0;
+            for (int ii = 0; ii < ni; ii += 4) {
+                double wk[4];
+                bool in[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double a = fma(-(double)(ii + q), hinv, xb);
+                    const double s = fma(a, a, bc2);
+                    in[q] = (s < 1.0) && (ii + q < ni);
+                    wk[q] = shape_s<KID>(s);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = r.lo[0] + ii + q;
                     const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
-                    sw = fma(kernel_shape<KID>(u), dx * dy * dz, sw);
-                    ++cnt;
+                    col = fma(select_or_zero(in[q], wk[q]), dx, col);
+                    cnt += in[q] ? 1 : 0;
                 }
             }
+            sw = fma(col, dy * dz, sw);
         }
     }
     sw = warp_sum(sw);
@@ -111,39 +124,72 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     const double volume_norm = kernel_norm * wpp * r.w * G.len2pix;   // :169
     const bool poison = !isfinite(volume_norm);
 
+    // ---- pass B (cic_3D.jl:172-188)
     const long long n = G.npix, npl = n * n * n;
+    if (fb || poison) {
+        // rare: wk := 1 over the whole box (no cell centre covered), or an Inf/NaN norm that marks the whole box
+        for (int kc = c0; kc < nk; kc += W) {
+            const int k = r.lo[2] + kc;
+            const double cz = center_dist(r.z, (double)k) * hinv;
+            const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
+            for (int jr = r0; jr < nj; jr += R) {
+                const int j = r.lo[1] + jr;
+                const double by = center_dist(r.y, (double)j) * hinv;
+                const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
+                for (int ii = 0; ii < ni; ++ii) {
+                    const int i = r.lo[0] + ii;
+                    const double a = fma(-(double)ii, hinv, xb);
+                    const double s = fma(a, a, fma(by, by, cz * cz)) + 1e-300;
+                    const double wk = fb ? 1.0 : ((s < 1.0) ? shape_s<KID>(s) : 0.0);
+                    const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
+                    const double pw = wk * (dx * dy * dz) * volume_norm;
+                    if (pw != 0.0) {
+                        const long long idx = (long long)i * n * n + (long long)j * n + k;
+                        red_add(image + npl + idx, pw);
+                        red_add(image + idx, r.q * pw);
+                        ++touched;
+                    }
+                }
+            }
+        }
+        return;
+    }
+    const double vq = volume_norm * r.q;
+    const bool live_p = nonzero_bits(volume_norm);
     for (int kc = c0; kc < nk; kc += W) {
         const int k = r.lo[2] + kc;
-        const double zd = center_dist(r.z, (double)k);
-        const double zd2 = __dmul_rn(zd, zd);
+        const double cz = center_dist(r.z, (double)k) * hinv;
         const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
         for (int jr = r0; jr < nj; jr += R) {
             const int j = r.lo[1] + jr;
-            const double yd = center_dist(r.y, (double)j);
-            const double yd2 = __dmul_rn(yd, yd);
+            const double by = center_dist(r.y, (double)j) * hinv;
+            const double bc2 = fma(by, by, cz * cz) + 1e-300;
+            if (bc2 >= 1.0 || !live_p) continue;
             const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
-            for (int ii = 0; ii < ni; ++ii) {
-                const int i = r.lo[0] + ii;
-                const double xd = center_dist(r.x, (double)i);
-                double wk;
-                if (fb)
-                    wk = 1.0;
-                else {
-                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(xd, xd), yd2), zd2);
-                    const double u = __dmul_rn(__dsqrt_rn(s), r.hinv);
-                    if (!(u <= 1.0)) {
-                        if (!poison) continue;  // see s2g_cic2d.cu: Inf/NaN norm marks the whole bounding box
-                        wk = 0.0;
-                    } else
-                        wk = kernel_shape<KID>(u);
+            const double dydz = dy * dz;
+            double* __restrict__ base = image + (long long)j * n + k;
+            for (int ii = 0; ii < ni; ii += 4) {
+                double wk[4];
+                bool in[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double a = fma(-(double)(ii + q), hinv, xb);
+                    const double s = fma(a, a, bc2);
+                    in[q] = (s < 1.0) && (ii + q < ni);
+                    wk[q] = shape_s<KID>(s);
                 }
-                const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
-                const double pw = wk * (dx * dy * dz) * volume_norm;
-                if (pw != 0.0) {
-                    const long long idx = (long long)i * n * n + (long long)j * n + k;  // indices.jl:15-17
-                    red_add(image + npl + idx, pw);
-                    red_add(image + idx, r.q * pw);
-                    ++touched;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!in[q]) continue;
+                    const int i = r.lo[0] + ii + q;
+                    const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
+                    const double g = wk[q] * (dx * dydz);
+                    if (nonzero_bits(g)) {
+                        const long long idx = (long long)i * n * n;  // indices.jl:15-17
+                        red_add(base + npl + idx, g * volume_norm);
+                        red_add(base + idx, g * vq);
+                        ++touched;
+                    }
                 }
             }
         }

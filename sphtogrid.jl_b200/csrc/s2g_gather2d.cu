@@ -60,68 +60,6 @@ __host__ __device__ constexpr double analytic_norm_min_h(int kid)
                                            : 1e300;
 }
 
-// 1/sqrt(s) for s > 0 to ~2 ulp: MUFU.RSQ64H seed + one third-order Newton step (no IEEE fix-up, no slow path)
-__device__ __forceinline__ double rsqrt_fast(double s)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    const double e = fma(-s, y * y, 1.0);
-    const double c = fma(e, 0.375, 0.5);
-    return fma(c, e * y, y);
-}
-
-// kernel shape as a function of t = 1 - u for 0 < t <= 1, WITHOUT range test (callers mask u >= 1).
-// The polynomial factor of the Wendland kernels is re-expanded in t (saves forming u); WendlandC8 keeps the u form
-// (its t-expansion has alternating coefficients ~4e3 and would lose ~3 digits to cancellation).
-template <int KID>
-__device__ __forceinline__ double shape_t(double t)
-{
-    if (KID == S2G_KERNEL_CUBIC) {
-        // u < 0.5: 1 + 6(u-1)u^2 = 1 - 6t + 12t^2 - 6t^3 ; else 2 t^3
-        const double a = fma(fma(fma(-6.0, t, 12.0), t, -6.0), t, 1.0), b = 2.0 * (t * t * t);
-        return t > 0.5 ? a : b;
-    } else if (KID == S2G_KERNEL_QUINTIC) {
-        const double b = fmax(t - 1.0 / 3.0, 0.0), c = fmax(t - 2.0 / 3.0, 0.0);
-        const double a2 = t * t, b2 = b * b, c2 = c * c;
-        return fma(15.0 * c, c2 * c2, fma(-6.0 * b, b2 * b2, a2 * a2 * t));
-    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
-        const double t2 = t * t;
-        return (t2 * t2) * fma(-4.0, t, 5.0);
-    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
-        const double t2 = t * t;
-        return (t2 * t2 * t2) * fma(fma(35.0 / 3.0, t, -88.0 / 3.0), t, 56.0 / 3.0);
-    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
-        const double t2 = t * t, t4 = t2 * t2;
-        return (t4 * t4) * fma(fma(fma(-32.0, t, 121.0), t, -154.0), t, 66.0);
-    } else {
-        const double t2 = t * t, t4 = t2 * t2, u = 1.0 - t;
-        return (t4 * t4 * t2) * fma(fma(fma(fma(429.0, u, 450.0), u, 210.0), u, 50.0), u, 5.0);
-    }
-}
-
-// w(sqrt(s)) for 0 < s < 1 (garbage for s >= 1: mask it): t = 1 - s * rsqrt(s)
-template <int KID>
-__device__ __forceinline__ double shape_s(double s)
-{
-    return shape_t<KID>(fma(-s, rsqrt_fast(s), 1.0));
-}
-
-// v if flag else +0.0, as a data select (keeps the four per-group dependency chains in one straight-line block;
-// a C++ ?: around the kernel evaluation invites the compiler to branch around it per lane)
-__device__ __forceinline__ double select_or_zero(bool flag, double v)
-{
-    double r;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
-        : "=d"(r)
-        : "d"(v), "r"((int)flag));
-    return r;
-}
-
-__device__ __forceinline__ bool nonzero_bits(double v)
-{
-    return ((__double2hiint(v) & 0x7fffffff) | __double2loint(v)) != 0;
-}
-
 // does the kernel support (circle of radius h around (x,y)) possibly reach a pixel centre of tile (ti,tj)?
 // conservative (never rejects a tile that holds a pixel with u < 1); evaluated on the GRec fields by BOTH the pair
 // count (k_norm2d) and the pair expansion (k_expand), so the two always agree.
