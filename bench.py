@@ -41,6 +41,8 @@ WORKLOADS = {
                 desc="8M particles of the c3 stream, 512^3 (debug)", n_stream=64 * 1024 * 1024),
     "c5": dict(n=1024 * 1024 * 1024, npix=8192, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=5,
                desc="synthetic 1B-particle box, 8192^2 2D map, WendlandC6"),
+    "c5s": dict(n=32 * 1024 * 1024, npix=8192, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=5,
+                desc="32M particles of the c5 stream (hsml of the 1B set), 8192^2 (debug)", n_stream=1024 * 1024 * 1024),
     "small": dict(n=1 << 20, npix=1024, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=2,
                   desc="1M particles, 1024^2 (debug)"),
 }

@@ -102,8 +102,8 @@ S2G_API const char* s2g_version(void);
 S2G_API int s2g_set_stream(s2g_ctx* ctx, void* cuda_stream);
 S2G_API int s2g_set_strategy(s2g_ctx* ctx, int strategy /* s2g_strategy */);
 /* Pass A of the 2D deposit (calculate_weights, cic_2D.jl:11-72) sums w(u)*dA over the footprint.  For footprints
- * that are not clipped by the image and resolved by >= 32..96 pixels per kernel radius (kernel dependent) that sum
- * equals h^2 * ∫w(u) 2πu du to better than 2e-13 relative (tools/analytic_norm_study.py) and the closed form is
+ * that are not clipped by the image and resolved by >= 20..64 pixels per kernel radius (kernel dependent) that sum
+ * equals h^2 * ∫w(u) 2πu du to better than 5e-12 relative (tools/analytic_norm_study.py) and the closed form is
  * used by default.  on != 0 forces the numerical sum for every particle. */
 S2G_API int s2g_set_exact_norm(s2g_ctx* ctx, int on);
 S2G_API int s2g_get_stats(s2g_ctx* ctx, s2g_stats* out);

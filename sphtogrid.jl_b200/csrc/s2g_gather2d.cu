@@ -50,13 +50,14 @@ __host__ __device__ constexpr double shape_integral_2d(int kid)
 }
 
 // smallest h [pixels] from which the discrete pass-A sum of an UNCLIPPED footprint equals h^2 * shape_integral to
-// better than 2e-13 relative (tools/analytic_norm_study.py; Poisson summation).  Infinity: never use the integral.
+// better than 5e-12 relative — a 20th of the 1e-10 parity budget (tools/analytic_norm_study.py; Poisson summation:
+// the difference is the kernel's Fourier transform at the pixel frequency).  Infinity: never use the integral.
 __host__ __device__ constexpr double analytic_norm_min_h(int kid)
 {
-    return kid == S2G_KERNEL_WENDLAND_C8   ? 32.0
-           : kid == S2G_KERNEL_WENDLAND_C6 ? 48.0
-           : kid == S2G_KERNEL_WENDLAND_C4 ? 96.0
-           : kid == S2G_KERNEL_QUINTIC     ? 96.0
+    return kid == S2G_KERNEL_WENDLAND_C8   ? 20.0
+           : kid == S2G_KERNEL_WENDLAND_C6 ? 32.0
+           : kid == S2G_KERNEL_WENDLAND_C4 ? 56.0
+           : kid == S2G_KERNEL_QUINTIC     ? 64.0
                                            : 1e300;
 }
 
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 if (rlo > rhi || g.jMax < jw0 || g.jMin > jw0 + 15) continue;
                 const double hinv = g.hinv;
                 const double bq = center_dist(g.y, jd) * hinv;
-                const double b2 = fmax(bq * bq, 1e-300);  // s > 0 even when a pixel centre sits on the particle
+                const double b2 = fma(bq, bq, 1e-300);  // s > 0 even when a pixel centre sits on the particle
                 const double dy = (j == g.jMin) ? g.dy_lo : ((j == g.jMax) ? g.dy_hi : 1.0);
                 const double dyan = dy * g.an;
                 // pix_weight != 0 test of cic_2D.jl:211 hoisted: wk > 0 inside the disc, so only dy*area_norm decides

@@ -211,7 +211,7 @@ def test_size_independent_properties_large(s2g):
 @pytest.mark.parametrize("kernel", ["WendlandC6", "WendlandC8", "WendlandC4", "Quintic", "Cubic"])
 def test_closed_form_normalisation_vs_numerical_sum(s2g, oracle, kernel):
     """Well-resolved, unclipped footprints use h^2*∫w instead of the pass-A sum (s2g_set_exact_norm).  Both modes must
-    agree with each other to ~1e-12 and with the oracle to the 1e-10 bar."""
+    agree with each other to 1e-11 (design bound 5e-12) and with the oracle to the 1e-10 bar."""
     rng = np.random.default_rng(17)
     n = 300
     npix = 1024
@@ -223,7 +223,7 @@ def test_closed_form_normalisation_vs_numerical_sum(s2g, oracle, kernel):
     c_exact = s2g.Context(0, strategy="gather", exact_norm=True)
     a = s2g.cic_mapping_2D(pos, hsml, m, rho, q, w, param=par, kernel=kern(s2g, kernel), ctx=c_fast)
     b = s2g.cic_mapping_2D(pos, hsml, m, rho, q, w, param=par, kernel=kern(s2g, kernel), ctx=c_exact)
-    assert_parity(a, b, rtol=2e-12, what="closed form vs numerical pass A")
+    assert_parity(a, b, rtol=1e-11, what="closed form vs numerical pass A")
     ref, _ = oracle.cic_mapping_2d(pos, hsml, m, rho, q, w, par.len2pix, npix, kernel, 2, True)
     assert_parity(a, ref, what="closed form vs oracle")
     assert_parity(b, ref, what="numerical vs oracle")

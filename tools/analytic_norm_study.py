@@ -3,7 +3,7 @@
 pass-A sum  Σ_ij w(u_ij) dA_ij  of cic_2D.jl:11-72 for a particle whose footprint is NOT clipped by the image?
 (Poisson summation: the difference is the kernel's Fourier transform at multiples of the pixel frequency, which
 falls off with the kernel's smoothness.)  Prints, per kernel, the worst relative difference over random sub-pixel
-offsets as a function of h [pixels]; the thresholds in csrc/s2g_gather2d.cu are where this stays below 2e-13."""
+offsets as a function of h [pixels]; the thresholds in csrc/s2g_gather2d.cu are where this stays below 5e-12."""
 import math
 import numpy as np
 
