@@ -227,16 +227,6 @@ def main():
     par2 = s2g.recentred_parameters(par)
     kid = getattr(s2g, wl["kernel"])(KERNEL_DIM[dims]).kernel_id
     healpix = dims == 0
-    if healpix:
-        # observer at the box centre; shell filter of filter_sort_particles done once, untimed, with torch ops
-        # (all particles that pass are handed to the deposit; the reference's sorted[mask] quirk is host logic)
-        rel = d_pos.view(n_loc, 3) - 0.5
-        rad = rel.norm(dim=1)
-        keep = (rad >= 0.05) & (rad <= 0.5)
-        d_pos = rel[keep].contiguous().view(-1)
-        d_h, d_m, d_rho, d_T = (t[keep].contiguous() for t in (d_h, d_m, d_rho, d_T))
-        n_loc = int(keep.sum())
-        del rel, rad, keep
     ncell = npix ** dims if not healpix else 12 * npix * npix
     planes = 2
     image = torch.empty(ncell * planes, dtype=f64, device=dev)
@@ -244,9 +234,16 @@ def main():
     q_t, w_t = (d_T, d_rho) if dims != 3 else (d_rho, d_one)
     shift, half = _lib.dbl3(par.center), _lib.dbl3(par2.halfsize)
 
+    hp_center = (C.c_double * 3)(0.5, 0.5, 0.5)          # observer at the box centre
+    hp_shell = (C.c_double * 2)(0.05, 0.5)               # radius_limits = [0.05 L, 0.5 L]
+    hp_nsel = C.c_int64(0)
+
     def step_healpix():
-        _lib.check(L.s2g_healpix_deposit_dev(ctx.handle, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1,
-                                             npix, kid, 1, 0, P(image), P(image[ncell:])))
+        # the whole healpix_map body on the device: Pos .-= center, shell filter, far-to-near selection
+        # (filter_sort_particles incl. its sorted[mask] semantics), particle loop
+        _lib.check(L.s2g_healpix_map_dev(ctx.handle, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc,
+                                         hp_center, hp_shell, npix, kid, 1, 0, P(image), P(image[ncell:]),
+                                         C.byref(hp_nsel)))
         if world > 1:
             dist.all_reduce(image)
 

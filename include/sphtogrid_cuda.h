@@ -194,6 +194,20 @@ S2G_API int s2g_healpix_deposit_dev(s2g_ctx* ctx, const void* pos, const void* h
                                     const void* binq, const void* w, int64_t n, int32_t in_dtype, int64_t nside,
                                     int32_t kernel, int32_t calc_mean, int32_t accumulate, double* map_dev,
                                     double* wmap_dev);
+/* ---- fused healpix_map body (src/healpix_interpolation/main.jl:92-227): `Pos .-= center`, shell filter and the
+ *      far-to-near selection of filter_sort_particles (filter_particles.jl:17-54, including its `sorted[mask]`
+ *      semantics) on the device, then the particle loop.  Float64 inputs only, like the reference (its methods are
+ *      `where T` over homogeneous Float64 arrays).  pos_recentred_out (optional): the recentred positions, for the
+ *      glue to reproduce the in-place mutation of Pos.  stats->n_in returns the number of particles in the shell.
+ *      The `calc_mean=false` BoundsError of the reference (filter_particles.jl:28-30) is raised by the host glue. */
+S2G_API int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                            const void* binq, const void* w, int64_t n, const double center[3],
+                            const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                            void* pos_recentred_out, double* map_out, double* wmap_out, s2g_stats* stats_or_null);
+S2G_API int s2g_healpix_map_dev(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                                const void* binq, const void* w, int64_t n, const double center[3],
+                                const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                                int32_t accumulate, double* map_dev, double* wmap_dev, int64_t* n_selected);
 /* pixel list of one particle (bit-exact contract vs the oracle): contributing_pixels (constributing_pixels.jl:7-22) */
 S2G_API int s2g_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, int64_t nside, int64_t* out,
                                int64_t cap, int64_t* count_out);

@@ -87,6 +87,9 @@ _SIGS = {
                                                           _i32, _i32, _vp]),
     "s2g_healpix_deposit": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i64, _i32, _i32, _vp, _vp, C.POINTER(Stats)]),
     "s2g_healpix_deposit_dev": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "s2g_healpix_map": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _dp, _dp, _i64, _i32, _i32, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "s2g_healpix_map_dev": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _dp, _dp, _i64, _i32, _i32, _i32, _vp, _vp,
+                                                        C.POINTER(C.c_int64)]),
     "s2g_healpix_pixels": (C.c_int, [_vp, _dp, _f64, _i64, _vp, _i64, C.POINTER(C.c_int64)]),
     "s2g_stencil_deposit": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _vp, C.POINTER(Stats)]),
     "s2g_stencil_deposit_dev": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _i32, _vp]),

@@ -689,7 +689,7 @@ extern "C" int s2g_healpix_deposit_dev(s2g_ctx* ctx, const void* pos, const void
         S2G_CUDA(cudaMemsetAsync(wmap_dev, 0, sizeof(double) * npix, ctx->stream));
     }
     s2g_particles P = dev_particles(pos, hsml, m, rho, binq, w, n, in_dtype);
-    return s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, map_dev, wmap_dev);
+    return s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, nullptr, map_dev, wmap_dev);
 }
 
 extern "C" int s2g_healpix_deposit(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
@@ -713,7 +713,7 @@ extern "C" int s2g_healpix_deposit(s2g_ctx* ctx, const void* pos, const void* hs
     S2G_TRY(stage_particles(ctx, pos, hsml, m, rho, binq, w, n, 1, in_dtype, P));
     S2G_CUDA(cudaMemsetAsync(dmaps, 0, sizeof(double) * npix * 2, ctx->stream));
     S2G_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    S2G_TRY(s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, dmap, dwmap));
+    S2G_TRY(s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, nullptr, dmap, dwmap));
     S2G_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     S2G_CUDA(cudaMemcpyAsync(map_out, dmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
     S2G_CUDA(cudaMemcpyAsync(wmap_out, dwmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
@@ -723,6 +723,82 @@ extern "C" int s2g_healpix_deposit(s2g_ctx* ctx, const void* pos, const void* hs
     ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
+    if (stats) *stats = ctx->stats;
+    return S2G_OK;
+}
+
+// fused healpix_map body: recentre on the observer + shell filter + far-to-near selection quirk + deposit
+extern "C" int s2g_healpix_map_dev(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                                   const void* binq, const void* w, int64_t n, const double center[3],
+                                   const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                                   int32_t accumulate, double* map_dev, double* wmap_dev, int64_t* n_selected)
+{
+    CTX_ENTER(ctx);
+    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, S2G_F64, 1.0, 1, kernel));
+    S2G_CHECK(nside >= 1 && nside <= 8192 && (nside & (nside - 1)) == 0, S2G_EINVAL,
+              "%s: nside must be a power of two in [1, 8192]", __func__);
+    S2G_CHECK(map_dev && wmap_dev && center && radius_limits, S2G_EINVAL, "%s: NULL argument", __func__);
+    S2G_TRY(stats_begin(ctx, n));
+    const size_t npix = (size_t)(12 * nside * nside);
+    if (!accumulate) {
+        S2G_CUDA(cudaMemsetAsync(map_dev, 0, sizeof(double) * npix, ctx->stream));
+        S2G_CUDA(cudaMemsetAsync(wmap_dev, 0, sizeof(double) * npix, ctx->stream));
+    }
+    s2g_particles P = dev_particles(pos, hsml, m, rho, binq, w, n, S2G_F64);
+    P.fuse_center = 1;  // Pos .-= center (Float64), no periodic wrap, no box filter
+    P.periodic = 0;
+    for (int d = 0; d < 3; ++d) { P.shift[d] = center[d]; P.halfsize[d] = 0.0; }
+    long long nsel = 0;
+    S2G_TRY(s2g_launch_healpix_filtered(ctx, P, radius_limits[0], radius_limits[1], nside, kernel, calc_mean, map_dev,
+                                        wmap_dev, &nsel));
+    if (n_selected) *n_selected = nsel;
+    return S2G_OK;
+}
+
+extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                               const void* binq, const void* w, int64_t n, const double center[3],
+                               const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                               void* pos_recentred_out, double* map_out, double* wmap_out, s2g_stats* stats)
+{
+    CTX_ENTER(ctx);
+    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, S2G_F64, 1.0, 1, kernel));
+    S2G_CHECK(nside >= 1 && nside <= 8192 && (nside & (nside - 1)) == 0, S2G_EINVAL,
+              "%s: nside must be a power of two in [1, 8192]", __func__);
+    S2G_CHECK(map_out && wmap_out && center && radius_limits, S2G_EINVAL, "%s: NULL argument", __func__);
+    S2G_TRY(stats_begin(ctx, n));
+    const size_t npix = (size_t)(12 * nside * nside);
+    void* dmaps;
+    S2G_TRY(s2g_scratch(ctx, "image", sizeof(double) * npix * 2, &dmaps));
+    double* dmap = (double*)dmaps;
+    double* dwmap = dmap + npix;
+    S2G_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    s2g_particles P;
+    S2G_TRY(stage_particles(ctx, pos, hsml, m, rho, binq, w, n, 1, S2G_F64, P));
+    S2G_CUDA(cudaMemsetAsync(dmaps, 0, sizeof(double) * npix * 2, ctx->stream));
+    S2G_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    P.fuse_center = 1;
+    P.periodic = 0;
+    for (int d = 0; d < 3; ++d) { P.shift[d] = center[d]; P.halfsize[d] = 0.0; }
+    long long nsel = 0;
+    S2G_TRY(s2g_launch_healpix_filtered(ctx, P, radius_limits[0], radius_limits[1], nside, kernel, calc_mean, dmap,
+                                        dwmap, &nsel));
+    S2G_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (pos_recentred_out && n > 0) {  // the reference recentres the caller's Pos in place (filter_particles.jl:20)
+        void* dpo;
+        S2G_TRY(s2g_scratch(ctx, "pos_out", 3 * (size_t)n * sizeof(double), &dpo));
+        S2G_TRY(s2g_launch_center_filter(ctx, P, dpo, nullptr));
+        S2G_CUDA(cudaMemcpyAsync(pos_recentred_out, dpo, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    }
+    S2G_CUDA(cudaMemcpyAsync(map_out, dmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    S2G_CUDA(cudaMemcpyAsync(wmap_out, dwmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    S2G_TRY(stats_collect(ctx));
+    ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
+    ctx->stats.n_in = nsel;  // particles selected by the shell filter
     if (stats) *stats = ctx->stats;
     return S2G_OK;
 }

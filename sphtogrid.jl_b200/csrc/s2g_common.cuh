@@ -229,7 +229,9 @@ int s2g_launch_reduce_2d(s2g_ctx* ctx, const double* image_dev, long long nx, lo
 int s2g_launch_reduce_3d(s2g_ctx* ctx, const double* image_dev, long long npix, int reduce_image, double* out_dev);
 int s2g_launch_center_filter(s2g_ctx* ctx, const s2g_particles& P, void* pos_out_dev, uint8_t* mask_dev);
 int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
-                       double* map_dev, double* wmap_dev);
+                       const unsigned char* take, double* map_dev, double* wmap_dev);
+int s2g_launch_healpix_filtered(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, long long nside,
+                                int kernel, int calc_mean, double* map_dev, double* wmap_dev, long long* n_selected);
 int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, long long nside, long long* out_dev,
                               long long cap, long long* count_dev);
 int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const void* q, long long n, int in_dtype,

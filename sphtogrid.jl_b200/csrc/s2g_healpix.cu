@@ -11,6 +11,8 @@
 // Instead of materialising a pixel list per particle (the reference heap-allocates a Vector per particle) the
 // warp walks the disc ring by ring: each ring contributes one contiguous (mod ring length) run of pixels, lanes
 // stride over the run.  The pixel containing the particle centre is added when the disc walk did not visit it.
+#include <cub/cub.cuh>
+
 #include "s2g_common.cuh"
 
 namespace {
@@ -449,6 +451,7 @@ __device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d,
 
 template <int KID>
 __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, int calc_mean,
+                                                    const unsigned char* __restrict__ take,
                                                     double* __restrict__ amap, double* __restrict__ wmap,
                                                     unsigned long long* __restrict__ counters)
 {
@@ -464,6 +467,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= P.n) break;
+        if (take && !take[p]) continue;        // not selected by filter_sort_particles
         const double q = ld_in(P.binq, p, P.in_dtype);
         if (!calc_mean && q == 0.0) continue;  // main.jl:160-165
         Disc d;
@@ -614,13 +618,14 @@ __global__ void k_healpix_pixels(double px, double py, double pz, double radius,
 }
 
 template <int KID>
-int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, double* amap, double* wmap)
+int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned char* take,
+                     double* amap, double* wmap)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const HpGeom g = make_hp(nside);
     int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 8);
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_healpix<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, g, calc_mean, amap, wmap, ctx->d_counters);
+    k_healpix<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, g, calc_mean, take, amap, wmap, ctx->d_counters);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
@@ -629,20 +634,101 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
 
 }  // namespace
 
-int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean, double* amap,
-                       double* wmap)
+int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
+                       const unsigned char* take, double* amap, double* wmap)
 {
     if (P.n <= 0) return S2G_OK;
     switch (kernel) {
-    case S2G_KERNEL_CUBIC: return launch_healpix_k<S2G_KERNEL_CUBIC>(ctx, P, nside, calc_mean, amap, wmap);
-    case S2G_KERNEL_QUINTIC: return launch_healpix_k<S2G_KERNEL_QUINTIC>(ctx, P, nside, calc_mean, amap, wmap);
-    case S2G_KERNEL_WENDLAND_C2: return launch_healpix_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, nside, calc_mean, amap, wmap);
-    case S2G_KERNEL_WENDLAND_C4: return launch_healpix_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, nside, calc_mean, amap, wmap);
-    case S2G_KERNEL_WENDLAND_C6: return launch_healpix_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, nside, calc_mean, amap, wmap);
-    case S2G_KERNEL_WENDLAND_C8: return launch_healpix_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, nside, calc_mean, amap, wmap);
+    case S2G_KERNEL_CUBIC: return launch_healpix_k<S2G_KERNEL_CUBIC>(ctx, P, nside, calc_mean, take, amap, wmap);
+    case S2G_KERNEL_QUINTIC: return launch_healpix_k<S2G_KERNEL_QUINTIC>(ctx, P, nside, calc_mean, take, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C2: return launch_healpix_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, nside, calc_mean, take, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C4: return launch_healpix_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, nside, calc_mean, take, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C6: return launch_healpix_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, nside, calc_mean, take, amap, wmap);
+    case S2G_KERNEL_WENDLAND_C8: return launch_healpix_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, nside, calc_mean, take, amap, wmap);
     }
     s2g_set_error("unknown kernel id %d", kernel);
     return S2G_EINVAL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter_sort_particles (src/healpix_interpolation/filter_particles.jl:17-54) on the device.
+// The reference selects `sorted[sel]` with sorted = reverse(sortperm(Δx)) and sel the shell mask IN ORIGINAL ORDER:
+// the particle deposited for every i with sel[i] is the one of rank i in the far-to-near order (quirk Q5).  When
+// every particle is in the shell this is simply "all of them" (no sort needed); otherwise a stable radix sort of
+// the radii gives the permutation and take[sorted[i]] = 1 for each selected i.  The deposit order is irrelevant.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_hp_radii(s2g_particles P, double r0, double r1,
+                                                  unsigned long long* __restrict__ keys, unsigned* __restrict__ idx,
+                                                  unsigned char* __restrict__ sel, unsigned long long* nsel)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    bool s = false;
+    if (p < P.n) {
+        const double x = ld_pos(P, p, 0), y = ld_pos(P, p, 1), z = ld_pos(P, p, 2);
+        // Δx = @. √(Pos[1,:]^2 + Pos[2,:]^2 + Pos[3,:]^2)
+        const double dx = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        s = (r0 <= dx) && (dx <= r1);
+        keys[p] = (unsigned long long)__double_as_longlong(dx);  // dx >= 0: the bit pattern orders like the value
+        idx[p] = (unsigned)p;
+        sel[p] = s ? 1 : 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(nsel, (unsigned long long)__popc(b));
+}
+
+__global__ void __launch_bounds__(256) k_hp_take(const unsigned* __restrict__ asc, const unsigned char* __restrict__ sel,
+                                                 long long n, unsigned char* __restrict__ take)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (sel[i]) take[asc[n - 1 - i]] = 1;  // sorted = reverse(sortperm(Δx)); sorted[i] is selected
+}
+}  // namespace
+
+int s2g_launch_healpix_filtered(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, long long nside,
+                                int kernel, int calc_mean, double* amap, double* wmap, long long* n_selected)
+{
+    if (P.n <= 0) { if (n_selected) *n_selected = 0; return S2G_OK; }
+    const long long n = P.n;
+    void *d_keys, *d_keys2, *d_idx, *d_idx2, *d_sel, *d_take, *d_tmp;
+    S2G_TRY(s2g_scratch(ctx, "hp_keys", sizeof(unsigned long long) * n, &d_keys));
+    S2G_TRY(s2g_scratch(ctx, "hp_idx", sizeof(unsigned) * n, &d_idx));
+    S2G_TRY(s2g_scratch(ctx, "hp_sel", (size_t)n, &d_sel));
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_PAIRS, 0, sizeof(unsigned long long), ctx->stream));
+    const int blocks = (int)((n + 255) / 256);
+    int ph = s2g_phase_begin(ctx, PH_PREP);
+    k_hp_radii<<<blocks, 256, 0, ctx->stream>>>(P, r0, r1, (unsigned long long*)d_keys, (unsigned*)d_idx,
+                                                (unsigned char*)d_sel, ctx->d_counters + CNT_PAIRS);
+    S2G_CUDA(cudaGetLastError());
+    unsigned long long h_nsel = 0;
+    S2G_CUDA(cudaMemcpyAsync(&h_nsel, ctx->d_counters + CNT_PAIRS, sizeof(h_nsel), cudaMemcpyDeviceToHost, ctx->stream));
+    s2g_phase_end(ctx, ph);
+    S2G_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    if (n_selected) *n_selected = (long long)h_nsel;
+    const unsigned char* take = nullptr;
+    if ((long long)h_nsel != n) {
+        S2G_TRY(s2g_scratch(ctx, "hp_keys2", sizeof(unsigned long long) * n, &d_keys2));
+        S2G_TRY(s2g_scratch(ctx, "hp_idx2", sizeof(unsigned) * n, &d_idx2));
+        S2G_TRY(s2g_scratch(ctx, "hp_take", (size_t)n, &d_take));
+        ph = s2g_phase_begin(ctx, PH_SORT);
+        size_t sb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned long long*)d_keys, (unsigned long long*)d_keys2,
+                                        (const unsigned*)d_idx, (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream);
+        S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
+        S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned long long*)d_keys,
+                                                 (unsigned long long*)d_keys2, (const unsigned*)d_idx,
+                                                 (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream));
+        S2G_CUDA(cudaMemsetAsync(d_take, 0, (size_t)n, ctx->stream));
+        k_hp_take<<<blocks, 256, 0, ctx->stream>>>((const unsigned*)d_idx2, (const unsigned char*)d_sel, n,
+                                                   (unsigned char*)d_take);
+        S2G_CUDA(cudaGetLastError());
+        s2g_phase_end(ctx, ph);
+        ctx->launches += 8;
+        take = (const unsigned char*)d_take;
+    }
+    return s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, take, amap, wmap);
 }
 
 int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, long long nside, long long* out,

@@ -56,8 +56,30 @@ def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), ra
     npix = 12 * int(Nside) ** 2
     if (not calc_mean) and np.sum(Bin_q) == 0:
         return np.zeros(npix), np.zeros(npix)
-    if _as_pos(Pos).dtype != np.float64:
+    pos = _as_pos(Pos)
+    if pos.dtype != np.float64:
         raise TypeError("healpix_map requires Float64 inputs (method signatures `where T`, pixel_weights.jl:87-91)")
-    pos, hsml, m, rho, bq, w = filter_sort_particles(Pos, Hsml, M, Rho, Bin_q, Weights, center, radius_limits,
-                                                     calc_mean)
-    return healpix_deposit(pos, hsml, m, rho, bq, w, Nside, kernel, calc_mean, ctx=ctx)
+    ctx = ctx or default_context()
+    n = pos.shape[0]
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    hs, mm, rr, bq, ww = f(Hsml), f(M), f(Rho), f(Bin_q), f(Weights)
+    if not calc_mean:
+        # filter_particles.jl:28-30: `sel = sel[Bin_q[sel] .> 0.0]` shortens the mask; indexing the permutation with
+        # it is a BoundsError unless every particle is in the shell AND has Bin_q > 0 (then nothing changes)
+        dx = np.sqrt((pos[:, 0] - center[0]) ** 2 + (pos[:, 1] - center[1]) ** 2 + (pos[:, 2] - center[2]) ** 2)
+        sel = find_in_shell(dx, radius_limits)
+        n_short = int(np.count_nonzero(bq[sel] > 0.0))
+        if n_short != n:
+            pos -= np.asarray(center, dtype=np.float64)[None, :]  # the reference has already recentred Pos by then
+            raise IndexError(f"BoundsError: attempt to access {n}-element Vector{{Int64}} at index "
+                             f"[{n_short}-element BitVector]")
+    amap = np.zeros(npix); wmap = np.zeros(npix)
+    pos_out = np.empty_like(pos)
+    cen = (C.c_double * 3)(*[float(c) for c in center])
+    rl = (C.c_double * 2)(float(radius_limits[0]), float(radius_limits[1]))
+    st = _lib.Stats()
+    check(lib().s2g_healpix_map(ctx.handle, ptr(pos), ptr(hs), ptr(mm), ptr(rr), ptr(bq), ptr(ww), n, cen, rl,
+                                int(Nside), _kernel_id(kernel), int(calc_mean), ptr(pos_out), ptr(amap), ptr(wmap),
+                                C.byref(st)))
+    pos[...] = pos_out  # Pos .-= center, in place (filter_particles.jl:20)
+    return amap, wmap

@@ -174,3 +174,26 @@ def test_stencils_parity(s2g, oracle, order, dims, periodic):
             assert math.isclose(got[:, 1].sum(), pos.shape[0], rel_tol=1e-12)
     avg = fn(pos, q, param=par, dimensions=dims, average=True, periodic=periodic)
     assert_parity(avg.ravel(), oracle.stencil_average(ref), rtol=1e-12, what="average")
+
+
+def test_healpix_map_device_filter_sort_quirk(s2g, oracle):
+    """healpix_map with a shell that does NOT contain every particle: the reference deposits `sorted[mask]` (mask in
+    original order applied to the far-to-near permutation, filter_particles.jl:33-41); the device path reproduces
+    exactly that selection (stable radix sort of the radii)."""
+    rng = np.random.default_rng(12)
+    n = 4000
+    pos = rng.normal(size=(n, 3)) * 40.0 + np.array([10.0, -5.0, 3.0])
+    pos[::7] = pos[1::7][: len(pos[::7])]          # exact ties in the radii (stable-sort order matters)
+    hsml = rng.random(n) * 3.0 + 0.5
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 10 + 1; w = rng.random(n) + 0.5
+    center = np.array([10.0, -5.0, 3.0])
+    for rl in ([20.0, 60.0], [0.0, 45.0], [0.0, np.inf]):
+        p1, p2 = pos.copy(), pos.copy()
+        a, wm = s2g.healpix_map(p1, hsml, m, rho, q, w, center=center, radius_limits=rl, Nside=64,
+                                kernel=s2g.WendlandC4(2), show_progress=False)
+        ra, rw = oracle.healpix_map(p2, hsml, m, rho, q, w, center=center, radius_limits=rl, nside=64,
+                                    kernel="WendlandC4")
+        assert np.array_equal(p1, p2)
+        assert_parity(wm, rw, rtol=1e-9, what=f"healpix_map weights, shell {rl}")
+        assert_parity(a, ra, rtol=1e-9, what=f"healpix_map map, shell {rl}")
+        assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12)
