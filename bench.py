@@ -299,7 +299,9 @@ def main():
                         st["n_launches"] + 1], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(cnt)
-    n_mapped, fpx, touched, pairs, launches = [int(x) for x in cnt.tolist()]
+    n_mapped, fpx_all, touched_all, pairs, launches = [int(x) for x in cnt.tolist()]
+    # the roofline describes ONE kernel launch on ONE GPU: use this rank's own counters there
+    fpx, touched = int(st["footprint_pixels"]), int(st["touched_pixels"])
     value = n_mapped / (ms_step * 1e-3) / 1e6
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the reduced map, all inside the timed region
@@ -389,7 +391,8 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "particles": n_total, "npix": npix, "kernel": wl["kernel"],
                            "strategy": args.strategy, "l2": "inputs (%.2f GB/rank) larger than L2" % (n_loc * 64 / 1e9),
-                           "mapped_particles": n_mapped, "pairs": pairs},
+                           "mapped_particles": n_mapped, "pairs": pairs,
+                           "footprint_pixels_all_ranks": fpx_all, "touched_pixels_all_ranks": touched_all},
                 "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_ms_per_step": wall_step}
         print(json.dumps(line), flush=True)
