@@ -270,18 +270,22 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
 
 def map_it(pos_in, hsml, mass, rho, bin_q, weights, RM=None, *, param: mappingParameters, kernel=None, snap=0,
            units="", image_prefix="dummy", reduce_image=True, parallel=True, calc_mean=True, show_progress=True,
-           sort_z=False, stokes=False, renorm=False, projection="xy", write_fits=False):
-    """Small helper to copy positions and map particles (cic_interpolation.jl:312-384).  The FITS write of the
-    reference is outside the hot path; the map is returned instead."""
+           sort_z=False, stokes=False, renorm=False, projection="xy", write_fits=True):
+    """Small helper function to copy positions, map particles and save the fits file
+    (cic_interpolation.jl:312-384).  Writes `image_prefix.<projection>.fits` like the reference and also returns the
+    map.  `parallel=True` shards over the ranks of an initialised process group (serial otherwise)."""
     from .kernels import WendlandC6
     kernel = kernel or WendlandC6(2)
-    pos = np.array(_as_pos(pos_in), copy=True)
+    pos = np.array(_as_pos(pos_in), copy=True)   # pos = copy(pos_in): the caller's positions stay untouched
     if projection != "xy":
         raise NotImplementedError("projection rotation is a pre-step outside the deposit path (SURVEY.md §8 f3)")
     import torch.distributed as dist
-    par_ok = parallel and dist.is_available() and dist.is_initialized()
+    par_ok = bool(parallel) and dist.is_available() and dist.is_initialized()
     m = sphMapping(pos, hsml, mass, rho, bin_q, weights, RM, param=param, kernel=kernel, show_progress=show_progress,
                    parallel=par_ok, reduce_image=reduce_image, calc_mean=calc_mean, sort_z=sort_z, stokes=stokes)
     if renorm:
         m /= np.max(m)
+    if write_fits and (not par_ok or dist.get_rank() == 0):
+        from .io import write_fits_image
+        write_fits_image(f"{image_prefix}.{projection}.fits", m, param, snap=snap, units=units)
     return m

@@ -275,3 +275,24 @@ def test_non_finite_normalisation_marks_bounding_box(s2g, oracle, strategy):
     fin = np.isfinite(ref)
     assert_parity(np.where(fin, got, 0.0), np.where(fin, ref, 0.0), what="finite part")
     ctx.close()
+
+
+def test_map_it_like_the_precompile_workload(s2g, oracle, tmp_path):
+    """src/precompile.jl:27-57: map_it on 100 random particles, 256^2, WendlandC4/C6, FITS out; positions untouched."""
+    rng = np.random.default_rng(100)
+    cic_pos = 15.0 * (rng.random((100, 3)) - 0.5)
+    cic_hsml = 2.0 * rng.random(100); cic_mass = rng.random(100); cic_rho = rng.random(100) + 1e-3
+    cic_T = 1.0e8 * rng.random(100)
+    kw = dict(center=[0.0, 0.0, 0.0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=256)
+    par = s2g.mappingParameters(**kw)
+    for kname in ("WendlandC4", "WendlandC6"):
+        p0 = cic_pos.copy()
+        m = s2g.map_it(p0, cic_hsml, cic_mass, cic_rho, cic_T, cic_rho, units="T", param=par, reduce_image=True,
+                       parallel=False, show_progress=False, snap=0, image_prefix=str(tmp_path / "dummy"),
+                       kernel=getattr(s2g, kname)(2))
+        assert np.array_equal(p0, cic_pos)
+        ref = oracle.sph_mapping(cic_pos.copy(), cic_hsml, cic_mass, cic_rho, cic_T, cic_rho,
+                                 param=oracle.mapping_parameters(**kw), kernel=kname, calc_mean=True)
+        assert_parity(m, ref, what="map_it " + kname)
+        d, _, _, units = s2g.read_fits_image(str(tmp_path / "dummy") + ".xy.fits")
+        assert np.array_equal(d, m[:, :, 0]) and units == "T"
