@@ -107,6 +107,77 @@ __global__ void __launch_bounds__(256) k_build_lists(const int* __restrict__ cls
     if (c == 2) list_g[pos_g[t]] = (int)(p0 + t);
 }
 
+// Σ w(u)·dA over the pixel centres inside the kernel, for the pixel rectangle [ia,ib] x [ja,jb] (indices may lie
+// outside the image: "virtual" pixels), optionally EXCLUDING the image [0,npix)².  Lanes own columns, rows are walked
+// four at a time.  dA = dx·dy with dx, dy = 1 except in the first/last row/column of the UNCLIPPED footprint
+// (iEl, iEh, jEl, jEh), where the overlap lengths dxl, dxh, dyl, dyh apply (get_dxyz, cic_shared.jl:60-62).
+// Returns this lane's partial sum; c counts the pixels inside.
+template <int KID>
+__device__ __forceinline__ double pass_a_region(double x, double y, double h, double hinv, int lane, int ia, int ib,
+                                                int ja, int jb, int iEl, int iEh, double dxl, double dxh, int jEl,
+                                                int jEh, double dyl, double dyh, bool excl, int npix, int& c)
+{
+    double acc = 0.0;
+    const int nj = jb - ja + 1;
+    const double xb = center_dist(x, (double)ia) * hinv;  // a(i) = xb - (i - ia)*hinv  (origin at ia: no cancellation)
+    for (int jc = lane; jc < ((nj + 31) & ~31); jc += 32) {
+        const int j = ja + jc;
+        const bool col = jc < nj;
+        const double b = center_dist(y, (double)j) * hinv;
+        const double b2 = col ? b * b : 4.0;
+        const double dy = (j == jEl) ? dyl : ((j == jEh) ? dyh : 1.0);
+        // rows that can reach this 32-column group: a² < 1 - min_lanes(b²)
+        double m = b2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m >= 1.0) continue;
+        const double reach = sqrt(1.0 - m) * h + 1.0;
+        const int r_lo = max(ia, (int)floor(x - 0.5 - reach));
+        const int r_hi = min(ib, (int)ceil(x - 0.5 + reach));
+        const bool jin = excl && (j >= 0) && (j < npix);
+        // all columns of the group inside the image: only the rows above and below the image remain
+        const bool all_in = excl && __all_sync(0xffffffffu, jin || !col);
+        const double b2s = fmax(b2, 1e-300);  // keeps s > 0 when a pixel centre sits on the particle
+        double colsum = 0.0;
+        for (int part = 0; part < 2; ++part) {
+            int lo = r_lo, hi = r_hi;
+            if (all_in) {
+                if (part == 0) hi = min(hi, -1); else lo = max(lo, npix);
+            } else if (part == 1)
+                break;
+            for (int i0 = lo; i0 <= hi; i0 += 4) {
+                double wk[4];
+                bool in[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 + k;
+                    const double a = fma(-(double)(i - ia), hinv, xb);
+                    const double s = fma(a, a, b2s);
+                    in[k] = (s < 1.0) && (i <= hi) && !(jin && i >= 0 && i < npix);
+                    wk[k] = shape_s<KID>(s);
+                }
+                if (i0 <= iEl || i0 + 3 >= iEh) {  // group touches the first / last row: partial overlaps
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + k;
+                        const double dx = (i == iEl) ? dxl : ((i == iEh) ? dxh : 1.0);
+                        colsum = fma(select_or_zero(in[k], wk[k]), dx, colsum);
+                        c += in[k] ? 1 : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        colsum += select_or_zero(in[k], wk[k]);
+                        c += in[k] ? 1 : 0;
+                    }
+                }
+            }
+        }
+        acc = fma(colsum, dy, acc);
+    }
+    return acc;
+}
+
 // ---- pass A for gather particles (cic_2D.jl:11-72): one warp per particle.
 // distr_weight = Σ w(u)·dA over the pixel centres inside the kernel.  Work in units of h: with a = (x-i-0.5)/h,
 // b = (y-j-0.5)/h a pixel is inside iff a²+b² < 1.  Lanes own columns, rows are walked four at a time (independent
@@ -136,59 +207,30 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
         // clipped by the image border?  (unclipped: the bounds are the plain floors of x±h)
         const bool unclipped = floor_to_int(r.x - r.h) >= 0 && floor_to_int(r.x + r.h) <= n1 &&
                                floor_to_int(r.y - r.h) >= 0 && floor_to_int(r.y + r.h) <= n1;
-        double sw;
+        // first/last row and column of the UNCLIPPED footprint and their overlap lengths
+        const int iEl = floor_to_int(r.x - r.h), iEh = floor_to_int(r.x + r.h);
+        const int jEl = floor_to_int(r.y - r.h), jEh = floor_to_int(r.y + r.h);
+        const double dxl = overlap_1d(r.x, r.h, iEl), dxh = overlap_1d(r.x, r.h, iEh);
+        const double dyl = overlap_1d(r.y, r.h, jEl), dyh = overlap_1d(r.y, r.h, jEh);
+        const bool resolved = !exact_norm && r.h >= analytic_norm_min_h(KID);
+        const double closed = r.h * r.h * shape_integral_2d(KID);
+        double sw = -1.0;
         long long cnt = 1;
-        if (!exact_norm && unclipped && r.h >= analytic_norm_min_h(KID)) {
-            sw = r.h * r.h * shape_integral_2d(KID);
-        } else {
-            double acc = 0.0;
+        if (resolved && unclipped) {
+            sw = closed;
+        } else if (resolved) {
+            // clipped by the image border: the sum over ALL lattice pixels of the unclipped footprint equals the closed
+            // form; subtract the (smaller) numerical sum over the virtual pixels that lie OUTSIDE the image
             int c = 0;
-            const double xb = (r.x - (double)r.iMin - 0.5) * r.hinv;  // a of the first row
-            for (int jc = lane; jc < ((nj + 31) & ~31); jc += 32) {
-                const int j = r.jMin + jc;
-                const bool col = jc < nj;
-                const double b = center_dist(r.y, (double)j) * r.hinv;
-                const double b2 = col ? b * b : 4.0;
-                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
-                // rows that can reach this 32-column group: a² < 1 - min_lanes(b²)
-                double m = b2;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (m >= 1.0) continue;
-                const double reach = sqrt(1.0 - m) * r.h + 1.0;
-                const int r_lo = max(0, (int)floor(r.x - 0.5 - reach) - r.iMin);
-                const int r_hi = min(ni - 1, (int)ceil(r.x - 0.5 + reach) - r.iMin);
-                double colsum = 0.0;
-                const double b2s = fmax(b2, 1e-300);  // keeps s > 0 when a pixel centre sits on the particle
-                for (int ir = r_lo; ir <= r_hi; ir += 4) {
-                    double wk[4];
-                    bool in[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double a = fma(-(double)(ir + k), r.hinv, xb);
-                        const double s = fma(a, a, b2s);
-                        in[k] = (s < 1.0) && (ir + k <= r_hi);
-                        wk[k] = shape_s<KID>(s);
-                    }
-                    if (ir == 0 || ir + 3 >= ni - 1) {  // group touches the first / last row: partial overlaps
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = r.iMin + ir + k;
-                            const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
-                            colsum = fma(select_or_zero(in[k], wk[k]), dx, colsum);
-                            c += in[k] ? 1 : 0;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            colsum += select_or_zero(in[k], wk[k]);
-                            c += in[k] ? 1 : 0;
-                        }
-                    }
-                }
-                acc = fma(colsum, dy, acc);
-            }
-            sw = warp_sum(acc);
+            const double out = warp_sum(pass_a_region<KID>(r.x, r.y, r.h, r.hinv, lane, iEl, iEh, jEl, jEh, iEl, iEh,
+                                                           dxl, dxh, jEl, jEh, dyl, dyh, true, (int)G.npix, c));
+            // keep the subtraction well conditioned: if little of the kernel is left inside, sum directly instead
+            if (out < 0.75 * closed) sw = closed - out;
+        }
+        if (sw < 0.0) {
+            int c = 0;
+            sw = warp_sum(pass_a_region<KID>(r.x, r.y, r.h, r.hinv, lane, r.iMin, r.iMax, r.jMin, r.jMax, iEl, iEh, dxl,
+                                             dxh, jEl, jEh, dyl, dyh, false, (int)G.npix, c));
             cnt = __reduce_add_sync(0xffffffffu, c);
         }
         GRec g;
