@@ -197,3 +197,31 @@ def test_healpix_map_device_filter_sort_quirk(s2g, oracle):
         assert_parity(wm, rw, rtol=1e-9, what=f"healpix_map weights, shell {rl}")
         assert_parity(a, ra, rtol=1e-9, what=f"healpix_map map, shell {rl}")
         assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12)
+
+
+def test_size_independent_properties_3d_and_healpix_large(s2g):
+    """Properties that hold at any size, checked well beyond what the oracle finishes quickly:
+    3D: Σ weight plane = Σ_p w·(m/ρ)·len2pix⁴ for unclipped particles (volume_norm identity, cic_3D.jl:167-188) and
+    linearity in the mapped quantity; HEALPix: Σ weight map = Σ_p w·(m/ρ)/(ang_pix·Δx)² (main.jl:32-38, 188-193)."""
+    n = 400000
+    pos, hsml, m, rho, q, w = random_particles(81, n, box=7.0, hmin=0.05, hmax=0.45)
+    npix = 160
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=npix)
+    a = s2g.cic_mapping_3D(pos, hsml, m, rho, q, w, param=par, kernel=s2g.WendlandC6(3))
+    expect = np.sum(w * m / rho * par.len2pix ** 4)
+    assert math.isclose(a[:, 1].sum(), expect, rel_tol=1e-11)
+    b = s2g.cic_mapping_3D(pos, hsml, m, rho, -2.5 * q, w, param=par, kernel=s2g.WendlandC6(3))
+    assert_parity(b[:, 0], -2.5 * a[:, 0], rtol=1e-12, what="3D linearity")
+    assert_parity(b[:, 1], a[:, 1], rtol=1e-12, what="3D weight plane independent of the quantity")
+    # HEALPix
+    nside = 512
+    ang = math.sqrt(4 * math.pi / (12 * nside * nside))
+    rng = np.random.default_rng(82)
+    hp = rng.normal(size=(200000, 3)) * 80.0
+    dist = np.linalg.norm(hp, axis=1)
+    hh = np.minimum(rng.random(200000) * 2.0 + 0.05, 0.9 * dist)
+    mm = rng.random(200000) + 0.5; rr = rng.random(200000) + 0.5; qq = rng.random(200000); ww = rng.random(200000) + 0.5
+    amap, wmap = s2g.healpix_deposit(hp, hh, mm, rr, qq, ww, nside, s2g.WendlandC4(2), True)
+    expect = np.sum(ww * (mm / rr) / (ang * dist) ** 2)
+    assert math.isclose(wmap.sum(), expect, rel_tol=1e-11)
+    assert math.isclose(amap.sum(), np.sum(qq * ww * (mm / rr) / (ang * dist) ** 2), rel_tol=1e-11)
