@@ -233,7 +233,8 @@ S2G_API int s2g_synth_particles_dev(s2g_ctx* ctx, uint64_t seed, int64_t first_i
 
 /* ---- roofline denominators measured live (bench.py): returns the achieved rate of a microbenchmark.
  *      which: 0 = FP64 DFMA [GFLOP/s], 1 = coalesced red.global.add.f64 [Gred/s] (32 consecutive doubles/warp,
- *      footprint `bytes`), 2 = random-address red.f64 [Gred/s], 3 = HBM copy [GB/s]. */
+ *      footprint `bytes`), 2 = random-address red.f64 [Gred/s], 3 = HBM copy [GB/s], 4 = shared-memory f64 atomics,
+ *      5 / 6 = cp.reduce.async.bulk .add.f64 with 256-byte / 2-KiB operations [Gadd/s]. */
 S2G_API int s2g_microbench(s2g_ctx* ctx, int32_t which, uint64_t bytes, int32_t iters, double* rate_out);
 
 #ifdef __cplusplus

@@ -12,6 +12,7 @@
 // warp walks the disc ring by ring: each ring contributes one contiguous (mod ring length) run of pixels, lanes
 // stride over the run.  The pixel containing the particle centre is added when the disc walk did not visit it.
 #include <cub/cub.cuh>
+#include <cstdlib>
 
 #include "s2g_common.cuh"
 
@@ -357,6 +358,102 @@ __device__ __forceinline__ void hp_walk_ring(const DiscFast& f, const RingTrig& 
     n_in += nin;
 }
 
+// ---- pass B of a long run through the TMA: the warp stages the run's contributions (both maps) in shared memory,
+// piece by piece (256 pixels), and lane 0 adds each contiguous piece to the maps with cp.reduce.async.bulk .add.f64
+// (SASS UBLKRED) — 588 Gadd/s in 2-KiB operations against 272 Gred/s for per-lane red.global (profiles/
+// r1_microbench_bulk_reduce.json).  Bulk operations need 16-byte aligned addresses and sizes: the staging index keeps
+// the parity of the global pixel index, and an odd first / last pixel of a segment goes through red.global instead.
+constexpr int HP_PIECE = 256;                 // pixels per staged piece
+constexpr int HP_STAGE = HP_PIECE + 8;        // doubles per plane and slot (parity shifts)
+struct __align__(16) HpStage {
+    double v[2][2][HP_STAGE];                 // [slot][plane: 0 = q*pw, 1 = pw][pixel]
+};
+
+__device__ __forceinline__ void hp_bulk_add(double* gdst, const double* ssrc, int count)
+{
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(saddr), "r"(count * 8) : "memory");
+}
+
+template <int KID>
+__device__ __forceinline__ void hp_walk_ring_bulk(const DiscFast& f, const RingTrig& rt, double c0, double s0,
+                                                  double c32, double s32, int sp, int nr, int j0, int cnt, int lane,
+                                                  double area_norm, bool fb, double q, HpStage& st, int& piece_no,
+                                                  double* __restrict__ amap, double* __restrict__ wmap)
+{
+    const double ez = rt.ct - f.uz, ez2 = ez * ez;
+    const bool belt = (rt.inv_den == f.belt_inv_den);
+    for (int t0 = 0; t0 < cnt; t0 += HP_PIECE) {
+        const int len = min(HP_PIECE, cnt - t0);
+        // the piece covers in-ring indices js .. js+len-1 (mod nr): segment 1 = [js, e1), segment 2 = [0, len2) if it wraps
+        int js = j0 + t0;
+        if (js >= nr) js -= nr;
+        const int len1 = min(len, nr - js), len2 = len - len1;
+        const int par1 = (sp + js) & 1, par2 = sp & 1;
+        const int off2 = (len1 + par1 + 1) & ~1;   // staging offset of segment 2 (even)
+        const int slot = piece_no & 1;
+        if (piece_no >= 2) {  // the bulk group that read this slot two pieces ago must be done with it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        if (lane < len) {
+            int j = js + lane;
+            if (j >= nr) j -= nr;
+            double cp, sph;
+            if (belt && t0 == 0) {
+                cp = fma(c0, f.cl, -s0 * f.sl);
+                sph = fma(s0, f.cl, c0 * f.sl);
+            } else
+                sincospi(((double)(j + 1) - rt.off) * rt.inv_den, &sph, &cp);
+            for (int t = lane; t < len; t += 32) {
+                double A, wk;
+                bool inside;
+                hp_pixel<KID>(f, rt.st, ez2, cp, sph, A, wk, inside);
+                if (fb) wk = 1.0;
+                const double pw = area_norm * wk * A;
+                // staging position with the parity of the global pixel index; unaligned ends go through red.global
+                const bool seg2 = t >= len1;
+                const int k = seg2 ? t - len1 : t;              // index inside the segment
+                const int slen = seg2 ? len2 : len1, par = seg2 ? par2 : par1;
+                const bool head = (k == 0) && (par == 1);
+                const bool tail = (k == slen - 1) && (((par + slen) & 1) == 1);
+                if (head || tail) {
+                    red_add(amap + sp + j, q * pw);
+                    red_add(wmap + sp + j, pw);
+                } else {
+                    const int idx = (seg2 ? off2 : 0) + par + k;
+                    st.v[slot][0][idx] = q * pw;
+                    st.v[slot][1][idx] = pw;
+                }
+                const double c_new = fma(cp, c32, -sph * s32), s_new = fma(sph, c32, cp * s32);
+                cp = c_new; sph = s_new;
+                j += 32;
+                if (j >= nr) j -= nr;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            // aligned interior of segment 1: pixels js+par1 .. (even count)
+            const int a1 = par1, n1 = (len1 - par1) & ~1;
+            if (n1 > 0) {
+                hp_bulk_add(amap + sp + js + a1, &st.v[slot][0][2 * a1], n1);
+                hp_bulk_add(wmap + sp + js + a1, &st.v[slot][1][2 * a1], n1);
+            }
+            if (len2 > 0) {
+                const int a2 = par2, n2 = (len2 - par2) & ~1;
+                if (n2 > 0) {
+                    hp_bulk_add(amap + sp + a2, &st.v[slot][0][off2 + 2 * a2], n2);
+                    hp_bulk_add(wmap + sp + a2, &st.v[slot][1][off2 + 2 * a2], n2);
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++piece_no;
+    }
+}
+
 // per-warp staging of the set-up of up to 32 rings (one ring per lane), so that the expensive uniform part of the
 // disc walk (ring_above / atan2 / sqrt per ring) is computed ONCE per ring by one lane instead of by all 32
 struct RingBatch {
@@ -370,7 +467,8 @@ __device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d,
                                                  long long ring0, int nb, bool setup, int lane, double area_norm,
                                                  bool fb, double q, bool q_finite, double* __restrict__ amap,
                                                  double* __restrict__ wmap, double& sw, double& sa, long long& n_in,
-                                                 long long& n_tot, bool& found_c)
+                                                 long long& n_tot, bool& found_c, HpStage& stg, int& piece_no,
+                                                 bool use_bulk)
 {
     if (setup) {
         int cnt_l = 0;
@@ -411,6 +509,11 @@ __device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d,
             if (cnt == 0) continue;
             RingTrig rt;
             rt.st = rb.st[r]; rt.ct = rb.ct[r]; rt.off = rb.off[r]; rt.inv_den = rb.inv_den[r];
+            if (PASS_B && use_bulk && cnt >= 64 && q_finite) {
+                hp_walk_ring_bulk<KID>(f, rt, rb.c0[r], rb.s0[r], rb.c32[r], rb.s32[r], rb.sp[r], rb.nr[r], rb.j0[r], cnt,
+                                       lane, area_norm, fb, q, stg, piece_no, amap, wmap);
+                continue;
+            }
             hp_walk_ring<KID, PASS_B>(f, rt, rb.c0[r], rb.s0[r], rb.c32[r], rb.s32[r], rb.sp[r], rb.nr[r], rb.j0[r], cnt,
                                       lane, (int)d.cpix, area_norm, fb, q, q_finite, amap, wmap, sw, sa, n_in, found_c);
         }
@@ -452,12 +555,17 @@ __device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d,
 template <int KID>
 __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, int calc_mean,
                                                     const unsigned char* __restrict__ take,
+                                                    const unsigned* __restrict__ order, bool use_bulk,
                                                     double* __restrict__ amap, double* __restrict__ wmap,
                                                     unsigned long long* __restrict__ counters)
 {
-    __shared__ RingBatch s_rb[8];
+    extern __shared__ __align__(16) unsigned char hp_smem[];
+    RingBatch* s_rb = reinterpret_cast<RingBatch*>(hp_smem);
+    HpStage* s_st = reinterpret_cast<HpStage*>(hp_smem + 8 * sizeof(RingBatch));
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     RingBatch& rb = s_rb[wq];
+    HpStage& stg = s_st[wq];
+    int piece_no = 0;
     unsigned long long touched = 0, fallback = 0, mapped = 0;
     const double belt_inv_den = 1.0 / __dmul_rn(2.0, (double)g.nside);
     double lane_c, lane_s;
@@ -467,6 +575,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= P.n) break;
+        if (order) p = order[p];               // processing order: by sky region (L2 locality of the map updates)
         if (take && !take[p]) continue;        // not selected by filter_sort_particles
         const double q = ld_in(P.binq, p, P.in_dtype);
         if (!calc_mean && q == 0.0) continue;  // main.jl:160-165
@@ -501,7 +610,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         for (long long base = 0; base < nrings; base += 32) {
             const int nb = (int)min(32LL, nrings - base);
             hp_process_batch<KID, false>(g, d, f, rb, d.ring_first + base, nb, true, lane, 0.0, false, q, q_finite, amap,
-                                         wmap, sw, sa, n_in, n_tot, found_c);
+                                         wmap, sw, sa, n_in, n_tot, found_c, stg, piece_no, false);
             if (base + 32 < nrings) __syncwarp();
         }
         found_c = __any_sync(0xffffffffu, found_c);
@@ -569,7 +678,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
                 const int nb = (int)min(32LL, nrings - base);
                 __syncwarp();
                 hp_process_batch<KID, true>(g, d, f, rb, d.ring_first + base, nb, nrings > 32, lane, area_norm, fb, q,
-                                            q_finite, amap, wmap, d0, d1, l0, l1, b0);
+                                            q_finite, amap, wmap, d0, d1, l0, l1, b0, stg, piece_no, use_bulk);
             }
         }
         if (lane == 0) touched += (unsigned long long)n_tot;
@@ -582,6 +691,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         }
         if (lane == 0) ++mapped;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outstanding bulk reductions
     if (lane == 0) {
         if (touched) { atomicAdd(&counters[CNT_TOUCHED], touched); atomicAdd(&counters[CNT_FOOTPRINT], touched); }
         if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
@@ -617,15 +727,67 @@ __global__ void k_healpix_pixels(double px, double py, double pz, double radius,
     *count = n;
 }
 
+// sky-region key of a particle: its RING pixel at Nside 32 (12288 regions)
+__global__ void __launch_bounds__(256) k_hp_order_keys(s2g_particles P, HpGeom gc, unsigned* __restrict__ keys,
+                                                       unsigned* __restrict__ idx)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const double x = ld_pos(P, p, 0), y = ld_pos(P, p, 1), z = ld_pos(P, p, 2);
+    const double nrm = sqrt(x * x + y * y + z * z);
+    unsigned k = 0;
+    if (nrm > 0.0) {
+        double ph = atan2(y, x);
+        if (ph < 0) ph += kTwoPi;
+        k = (unsigned)hp_ang2pix_ring(gc, acos(z / nrm), ph);
+    }
+    keys[p] = k;
+    idx[p] = (unsigned)p;
+}
+
 template <int KID>
 int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned char* take,
                      double* amap, double* wmap)
 {
-    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const HpGeom g = make_hp(nside);
-    int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 8);
+    // processing order by sky region, so that the ~2400 particles in flight update a common few-MB patch of the maps
+    const unsigned* order = nullptr;
+    const char* e_ord = getenv("S2G_HP_ORDER");
+    const char* e_blk = getenv("S2G_HP_BULK");
+    // Both are OFF by default: measured on the c4s sample (2.2 M particles, Nside 2048) they cost time —
+    // 640 ms (off/off) vs 716 ms (bulk) vs 681 ms (ordered) vs 758 ms (both); profiles/r1_healpix_experiments.txt.
+    // The kernel is issue/latency bound there, not red-bound; sky-ordered particles also contend on the same pixels.
+    const bool want_order = e_ord ? atoi(e_ord) != 0 : false;
+    const bool use_bulk = e_blk ? atoi(e_blk) != 0 : false;
+    if (want_order && P.n >= 65536) {
+        void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
+        S2G_TRY(s2g_scratch(ctx, "hp_okeys", sizeof(unsigned) * P.n, &d_k));
+        S2G_TRY(s2g_scratch(ctx, "hp_okeys2", sizeof(unsigned) * P.n, &d_k2));
+        S2G_TRY(s2g_scratch(ctx, "hp_oidx", sizeof(unsigned) * P.n, &d_i));
+        S2G_TRY(s2g_scratch(ctx, "hp_oidx2", sizeof(unsigned) * P.n, &d_i2));
+        const int ph = s2g_phase_begin(ctx, PH_SORT);
+        k_hp_order_keys<<<(int)((P.n + 255) / 256), 256, 0, ctx->stream>>>(P, make_hp(32), (unsigned*)d_k, (unsigned*)d_i);
+        S2G_CUDA(cudaGetLastError());
+        size_t sb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                        (unsigned*)d_i2, (int)P.n, 0, 14, ctx->stream);
+        S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
+        S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                                 (unsigned*)d_i2, (int)P.n, 0, 14, ctx->stream));
+        s2g_phase_end(ctx, ph);
+        ctx->launches += 4;
+        order = (const unsigned*)d_i2;
+    }
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    const size_t smem = 8 * (sizeof(RingBatch) + sizeof(HpStage));
+    static bool attr_set = false;
+    if (!attr_set) {
+        S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 2);
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_healpix<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, g, calc_mean, take, amap, wmap, ctx->d_counters);
+    k_healpix<KID><<<max(blocks, 1), 256, smem, ctx->stream>>>(P, g, calc_mean, take, order, use_bulk, amap, wmap, ctx->d_counters);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;

@@ -245,6 +245,36 @@ __global__ void __launch_bounds__(256) k_mb_smem_atomic(double* out, int iters)
     if (tile[threadIdx.x] == -1.0) out[0] = 1.0;
 }
 
+// TMA bulk reduction: every warp stages NB doubles in shared memory and adds them to a pseudo-randomly chosen
+// NB*8-byte row of the buffer with ONE cp.reduce.async.bulk (.add.f64, SASS UBLKRED) issued by lane 0
+template <int NB>
+__global__ void __launch_bounds__(256) k_mb_bulk_red_rows(double* buf, unsigned long long rows, int iters)
+{
+    __shared__ __align__(128) double stage[8][2][NB];
+    const unsigned lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    unsigned long long s = w * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    for (int i = 0; i < iters; ++i) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const unsigned long long row = (s >> 20) % rows;
+        const int slot = i & 1;
+        if (i >= 2) {  // the bulk op issued two iterations ago has finished reading this slot
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        for (int k = lane; k < NB; k += 32) stage[wq][slot][k] = 1.0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(&stage[wq][slot][0]);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                         ::"l"(buf + row * NB), "r"(saddr), "r"(NB * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double* rate_out)
 {
     void* buf = nullptr;
@@ -267,7 +297,7 @@ int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double*
         *rate_out = ops / (ms * 1e-3) * 1e-9;  // GFLOP/s or Gatomic/s
         return S2G_OK;
     }
-    if (which == 1 || which == 2) {
+    if (which == 1 || which == 2 || which == 5 || which == 6) {
         if (bytes < 4096) bytes = 4096;
         S2G_TRY(s2g_scratch(ctx, "mb", bytes, &buf));
         S2G_CUDA(cudaMemsetAsync(buf, 0, bytes, ctx->stream));
@@ -276,13 +306,17 @@ int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double*
             S2G_CUDA(cudaEventRecord(a, ctx->stream));
             if (which == 1)
                 k_mb_red_rows<<<blocks, 256, 0, ctx->stream>>>((double*)buf, nd / 32, iters);
+            else if (which == 5)   // 256-byte bulk reductions
+                k_mb_bulk_red_rows<32><<<blocks, 256, 0, ctx->stream>>>((double*)buf, nd / 32, iters);
+            else if (which == 6)   // 2-KiB bulk reductions
+                k_mb_bulk_red_rows<256><<<blocks, 256, 0, ctx->stream>>>((double*)buf, nd / 256, iters);
             else
                 k_mb_red_random<<<blocks, 256, 0, ctx->stream>>>((double*)buf, nd, iters);
             S2G_CUDA(cudaEventRecord(b, ctx->stream));
             S2G_CUDA(cudaEventSynchronize(b));
             S2G_CUDA(cudaEventElapsedTime(&ms, a, b));
         }
-        *rate_out = (double)blocks * 256.0 * (double)iters / (ms * 1e-3) * 1e-9;  // Gred/s
+        *rate_out = (double)blocks * 256.0 * (double)iters * (which == 6 ? 8.0 : 1.0) / (ms * 1e-3) * 1e-9;  // Gadd/s
         return S2G_OK;
     }
     if (which == 3) {
