@@ -45,6 +45,8 @@ WORKLOADS = {
                 desc="32M particles of the c5 stream (hsml of the 1B set), 8192^2 (debug)", n_stream=1024 * 1024 * 1024),
     "tiny": dict(n=64 * 1024 * 1024, npix=4096, dims=2, kernel="WendlandC6", n_ngb=0.05, seed=6,
                  desc="64M particles with ~2-pixel kernels, 4096^2 (scatter regime)"),
+    "tinys": dict(n=4 * 1024 * 1024, npix=4096, dims=2, kernel="WendlandC6", n_ngb=0.05, seed=6,
+                  desc="4M particles of the tiny stream (profiling)", n_stream=64 * 1024 * 1024),
     "small": dict(n=1 << 20, npix=1024, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=2,
                   desc="1M particles, 1024^2 (debug)"),
 }

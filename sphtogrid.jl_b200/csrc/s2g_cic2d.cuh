@@ -69,7 +69,8 @@ __device__ __forceinline__ double overlap_1d(double x, double h, int i)
 {
     const double a = __dadd_rn(x, h), b = (double)(i + 1);
     const double c = __dadd_rn(x, -h), d = (double)i;
-    return __dadd_rn(fmin(a, b), -fmax(c, d));
+    // plain selects (fmin/fmax carry NaN handling that costs ~8 instructions each; a NaN here is garbage anyway)
+    return __dadd_rn(a < b ? a : b, -(c > d ? c : d));
 }
 
 // x - i - 0.5 evaluated left to right (get_x_dx, cic_shared.jl:73)
