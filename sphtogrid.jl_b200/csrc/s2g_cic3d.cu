@@ -2,6 +2,9 @@
 //
 // Replaces: cic_mapping_3D (src/cic_interpolation/cic_3D.jl:110-209), calculate_weights (:13-78),
 //           get_quantities_3D (:87-97), reduce_image_3D (src/cic_interpolation/reduce_image.jl:39-55).
+#include <cub/cub.cuh>
+#include <cstdlib>
+
 #include "s2g_cic2d.cuh"
 
 struct Rec3 {
@@ -197,7 +200,8 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
 }
 
 template <int KID>
-__global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, double* __restrict__ image,
+__global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, const unsigned* __restrict__ order,
+                                                   double* __restrict__ image,
                                                    unsigned long long* __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
@@ -209,7 +213,8 @@ __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, 
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= P.n) break;
         const long long end = min(base + CHUNK, P.n);
-        for (long long p = base; p < end; ++p) {
+        for (long long t = base; t < end; ++t) {
+            const long long p = order ? (long long)order[t] : t;
             Rec3 r;
             if (!make_rec3(P, G, p, r)) continue;
             if (lane == 0) {
@@ -230,15 +235,60 @@ __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, 
     }
 }
 
+// coarse spatial key of a particle: the 16^3-cell block holding its centre.  Particles are DEPOSITED in key order so
+// that the ~2400 particles in flight update a compact region of the grid: with random order every red row misses L2
+// (measured 474 GB of DRAM traffic for 2·10^10 reds on the c3s sample).
+__global__ void __launch_bounds__(256) k_order3d_keys(s2g_particles P, s2g_geom G, unsigned* __restrict__ keys,
+                                                      unsigned* __restrict__ idx)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const int nb = (int)((G.npix + 15) / 16);
+    unsigned key = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double x = fma(ld_pos(P, p, d), G.len2pix, G.half_n);
+        int b = (int)floor(x * (1.0 / 16.0));
+        b = min(max(b, 0), nb - 1);
+        key = key * (unsigned)nb + (unsigned)b;
+    }
+    keys[p] = key;
+    idx[p] = (unsigned)p;
+}
+
 template <int KID>
 static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double* image)
 {
+    const unsigned* order = nullptr;
+    const char* e_ord = getenv("S2G_3D_ORDER");
+    if ((e_ord ? atoi(e_ord) != 0 : true) && P.n >= 65536) {
+        void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
+        S2G_TRY(s2g_scratch(ctx, "o3_keys", sizeof(unsigned) * P.n, &d_k));
+        S2G_TRY(s2g_scratch(ctx, "o3_keys2", sizeof(unsigned) * P.n, &d_k2));
+        S2G_TRY(s2g_scratch(ctx, "o3_idx", sizeof(unsigned) * P.n, &d_i));
+        S2G_TRY(s2g_scratch(ctx, "o3_idx2", sizeof(unsigned) * P.n, &d_i2));
+        const int phs = s2g_phase_begin(ctx, PH_SORT);
+        k_order3d_keys<<<(int)((P.n + 255) / 256), 256, 0, ctx->stream>>>(P, G, (unsigned*)d_k, (unsigned*)d_i);
+        S2G_CUDA(cudaGetLastError());
+        const int nb = (int)((G.npix + 15) / 16);
+        int bits = 1;
+        while ((1LL << bits) < (long long)nb * nb * nb) ++bits;
+        size_t sb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                        (unsigned*)d_i2, (int)P.n, 0, bits, ctx->stream);
+        S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
+        S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                                 (unsigned*)d_i2, (int)P.n, 0, bits, ctx->stream));
+        s2g_phase_end(ctx, phs);
+        ctx->launches += 4;
+        order = (const unsigned*)d_i2;
+    }
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const int warps_needed = (int)std::min<long long>((P.n + 3) / 4, (long long)ctx->sm_count * 8 * 8);
     int blocks = max(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, image, ctx->d_counters);
+    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, order, image, ctx->d_counters);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
