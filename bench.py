@@ -45,6 +45,8 @@ WORKLOADS = {
                 desc="32M particles of the c5 stream (hsml of the 1B set), 8192^2 (debug)", n_stream=1024 * 1024 * 1024),
     "tiny": dict(n=64 * 1024 * 1024, npix=4096, dims=2, kernel="WendlandC6", n_ngb=0.05, seed=6,
                  desc="64M particles with ~2-pixel kernels, 4096^2 (scatter regime)"),
+    "c3big": dict(n=512 * 1024, npix=512, dims=3, kernel="Cubic", n_ngb=4096.0, seed=3,
+                  desc="512k particles with ~13-cell kernels, 512^3 (3D large-footprint regime)", n_stream=64 * 1024 * 1024),
     "tinys": dict(n=4 * 1024 * 1024, npix=4096, dims=2, kernel="WendlandC6", n_ngb=0.05, seed=6,
                   desc="4M particles of the tiny stream (profiling)", n_stream=64 * 1024 * 1024),
     "small": dict(n=1 << 20, npix=1024, dims=2, kernel="WendlandC6", n_ngb=295.0, seed=2,

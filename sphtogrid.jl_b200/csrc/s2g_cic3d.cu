@@ -5,40 +5,7 @@
 #include <cub/cub.cuh>
 #include <cstdlib>
 
-#include "s2g_cic2d.cuh"
-
-struct Rec3 {
-    double x, y, z, h, hinv, vol, w, q;
-    int lo[3], hi[3];
-};
-
-__device__ __forceinline__ bool make_rec3(const s2g_particles& P, const s2g_geom& G, long long p, Rec3& r)
-{
-    r.q = ld_in(P.binq, p, P.in_dtype);
-    if (r.q == 0.0 && !G.calc_mean) return false;  // cic_3D.jl:142
-    const double px = ld_pos(P, p, 0), py = ld_pos(P, p, 1), pz = ld_pos(P, p, 2);
-    if (P.fuse_center && !in_image(P, px, py, pz)) return false;
-    const double hs = ld_in(P.hsml, p, P.in_dtype);
-    const double mm = ld_in(P.m, p, P.in_dtype);
-    const double rh = ld_in(P.rho, p, P.in_dtype);
-    r.w = ld_in(P.w, p, P.in_dtype);
-    r.h = __dmul_rn(hs, G.len2pix);
-    r.hinv = __ddiv_rn(1.0, r.h);
-    r.vol = __ddiv_rn(mm, __ddiv_rn(rh, G.l3));
-    r.x = __dadd_rn(__dmul_rn(px, G.len2pix), G.half_n);
-    r.y = __dadd_rn(__dmul_rn(py, G.len2pix), G.half_n);
-    r.z = __dadd_rn(__dmul_rn(pz, G.len2pix), G.half_n);
-    const int n1 = (int)G.npix - 1;
-    const double c[3] = {r.x, r.y, r.z};
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        r.lo[d] = max(floor_to_int(__dadd_rn(c[d], -r.h)), 0);
-        r.hi[d] = min(floor_to_int(__dadd_rn(c[d], r.h)), n1);
-        ok = ok && (r.lo[d] <= r.hi[d]);
-    }
-    return ok;
-}
+#include "s2g_cic3d.cuh"
 
 // lanes: W wide along k (contiguous axis, indices.jl:15-17), 32/W deep along j; i is walked by the whole warp in groups
 // of four independent chains.  Coordinates in units of h: a cell centre is inside the kernel iff a²+b²+c² < 1
@@ -201,7 +168,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
 
 template <int KID>
 __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, const unsigned* __restrict__ order,
-                                                   double* __restrict__ image,
+                                                   long long n_list, double* __restrict__ image,
                                                    unsigned long long* __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
@@ -211,8 +178,8 @@ __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, 
         long long base = 0;
         if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= P.n) break;
-        const long long end = min(base + CHUNK, P.n);
+        if (base >= n_list) break;
+        const long long end = min(base + CHUNK, n_list);
         for (long long t = base; t < end; ++t) {
             const long long p = order ? (long long)order[t] : t;
             Rec3 r;
@@ -257,11 +224,13 @@ __global__ void __launch_bounds__(256) k_order3d_keys(s2g_particles P, s2g_geom 
 }
 
 template <int KID>
-static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double* image)
+static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list, long long n_list,
+                              double* image)
 {
-    const unsigned* order = nullptr;
+    if (n_list <= 0) return S2G_OK;
+    const unsigned* order = reinterpret_cast<const unsigned*>(list);
     const char* e_ord = getenv("S2G_3D_ORDER");
-    if ((e_ord ? atoi(e_ord) != 0 : true) && P.n >= 65536) {
+    if (!list && (e_ord ? atoi(e_ord) != 0 : true) && P.n >= 65536) {
         void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
         S2G_TRY(s2g_scratch(ctx, "o3_keys", sizeof(unsigned) * P.n, &d_k));
         S2G_TRY(s2g_scratch(ctx, "o3_keys2", sizeof(unsigned) * P.n, &d_k2));
@@ -284,27 +253,27 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
         order = (const unsigned*)d_i2;
     }
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int warps_needed = (int)std::min<long long>((P.n + 3) / 4, (long long)ctx->sm_count * 8 * 8);
+    const int warps_needed = (int)std::min<long long>((n_list + 3) / 4, (long long)ctx->sm_count * 8 * 8);
     int blocks = max(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, order, image, ctx->d_counters);
+    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, order, n_list, image, ctx->d_counters);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return S2G_OK;
 }
 
-int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image)
+int s2g_launch_scatter_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const int* list,
+                          long long n_list, double* image)
 {
-    if (P.n <= 0) return S2G_OK;
     switch (kernel) {
-    case S2G_KERNEL_CUBIC: return launch_scatter3d_k<S2G_KERNEL_CUBIC>(ctx, P, G, image);
-    case S2G_KERNEL_QUINTIC: return launch_scatter3d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, image);
-    case S2G_KERNEL_WENDLAND_C2: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, G, image);
-    case S2G_KERNEL_WENDLAND_C4: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, G, image);
-    case S2G_KERNEL_WENDLAND_C6: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, G, image);
-    case S2G_KERNEL_WENDLAND_C8: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, G, image);
+    case S2G_KERNEL_CUBIC: return launch_scatter3d_k<S2G_KERNEL_CUBIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_QUINTIC: return launch_scatter3d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C2: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C4: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C6: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C8: return launch_scatter3d_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, G, list, n_list, image);
     }
     s2g_set_error("unknown kernel id %d", kernel);
     return S2G_EINVAL;
