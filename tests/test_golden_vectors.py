@@ -1,0 +1,51 @@
+"""Committed golden vectors (tests/golden/oracle_vectors.npz, made by make_oracle_vectors.py): the oracle must keep
+reproducing them bit for bit (CPU), and the CUDA path must match them at the parity bar (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "oracle_vectors.npz"))
+ARGS = [G[k] for k in ("pos", "hsml", "m", "rho", "q", "w")]
+
+
+def test_oracle_reproduces_golden_vectors(oracle):
+    pos, hsml, m, rho, q, w = ARGS
+    Q = np.stack([q, np.sqrt(q + 1.0)], axis=1)
+    assert np.array_equal(oracle.cic_mapping_2d(pos, hsml, m, rho, Q, w, 6.4, 64, "WendlandC6", 2, True)[0],
+                          G["map2d_WendlandC6"])
+    assert np.array_equal(oracle.cic_mapping_2d(pos, hsml, m, rho, q, w, 6.4, 64, "Cubic", 2, False)[0],
+                          G["map2d_Cubic_nomean"])
+    assert np.array_equal(oracle.cic_mapping_3d(pos, hsml, m, rho, q, w, 2.0, 20, "WendlandC4", 3, False)[0],
+                          G["map3d_WendlandC4"])
+    a, wm, _ = oracle.healpix_deposit(G["hp_pos"], hsml * 12.0, m, rho, q, w, 16, "WendlandC4", 2, True)
+    assert np.array_equal(a, G["hp_map"]) and np.array_equal(wm, G["hp_wmap"])
+    assert np.array_equal(oracle.stencil_deposit(2, 3, pos, q, 2.0, 20, False), G["cic3d"])
+    assert np.array_equal(oracle.stencil_deposit(3, 2, pos, q, 6.4, 64, True), G["tsc2d"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["auto", "scatter", "gather"])
+def test_gpu_matches_golden_vectors(s2g, strategy):
+    pos, hsml, m, rho, q, w = ARGS
+    ctx = s2g.Context(0, strategy=strategy)
+    p2 = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=64)
+    p3 = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=20)
+    Q = np.stack([q, np.sqrt(q + 1.0)], axis=1)
+    assert_parity(s2g.cic_mapping_2D(pos, hsml, m, rho, Q, w, param=p2, kernel=s2g.WendlandC6(2), calc_mean=True, ctx=ctx),
+                  G["map2d_WendlandC6"], what="golden 2D WendlandC6 multi-image")
+    assert_parity(s2g.cic_mapping_2D(pos, hsml, m, rho, q, w, param=p2, kernel=s2g.Cubic(2), calc_mean=False, ctx=ctx),
+                  G["map2d_Cubic_nomean"], what="golden 2D Cubic calc_mean=false")
+    assert_parity(s2g.cic_mapping_3D(pos, hsml, m, rho, q, w, param=p3, kernel=s2g.WendlandC4(3), ctx=ctx),
+                  G["map3d_WendlandC4"], what="golden 3D")
+    a, wm = s2g.healpix_deposit(G["hp_pos"], hsml * 12.0, m, rho, q, w, 16, s2g.WendlandC4(2), True, ctx=ctx)
+    assert_parity(a, G["hp_map"], rtol=1e-9, what="golden healpix map")
+    assert_parity(wm, G["hp_wmap"], rtol=1e-9, what="golden healpix weights")
+    assert_parity(s2g.cic_deposit(pos, q, param=p3, dimensions=3, average=False, ctx=ctx), G["cic3d"], rtol=1e-12,
+                  what="golden CIC")
+    assert_parity(s2g.tsc_deposit(pos, q, param=p2, dimensions=2, average=False, periodic=True, ctx=ctx), G["tsc2d"],
+                  rtol=1e-12, what="golden TSC")
+    ctx.close()
