@@ -153,6 +153,33 @@ function healpix_deposit!(allsky_map, weight_map, pos::Matrix{Float64}, hsml::Ve
 end
 
 """
+    healpix_map_fused!(allsky_map, weight_map, Pos, Hsml, M, Rho, Bin_q, Weights; center, radius_limits, Nside,
+                       kernel, calc_mean)
+
+The whole body of `healpix_map` after the map allocation (src/healpix_interpolation/main.jl:123-213) in ONE call:
+`Pos .-= center` (Pos is mutated like `filter_sort_particles` does), shell filter, the far-to-near selection
+`sorted[sel]` and the particle loop, all on the device (s2g_healpix_map).  The `calc_mean == false` BoundsError of
+filter_particles.jl:28-30 must be raised by the caller before (it depends only on `Bin_q` and the shell mask).
+"""
+function healpix_map_fused!(allsky_map, weight_map, Pos::Matrix{Float64}, Hsml::Vector{Float64}, M::Vector{Float64},
+                            Rho::Vector{Float64}, Bin_q::Vector{Float64}, Weights::Vector{Float64};
+                            center::Vector{<:Real}, radius_limits::Vector{<:Real}, Nside::Integer,
+                            kernel::AbstractSPHKernel, calc_mean::Bool=true, ctx::Context=default_context())
+    a, w = allsky_map.pixels, weight_map.pixels
+    cen = Float64.(center); rl = Float64.(radius_limits)
+    pos_out = similar(Pos)
+    GC.@preserve Pos Hsml M Rho Bin_q Weights a w cen rl pos_out begin
+        check(ccall((:s2g_healpix_map, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                     Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, Pos, Hsml, M, Rho, Bin_q, Weights, length(Hsml), cen, rl, Nside, kernel_id(kernel),
+                    calc_mean, pos_out, a, w, C_NULL))
+    end
+    Pos .= pos_out
+    return allsky_map, weight_map
+end
+
+"""
     sphmap_fused(Pos, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions, calc_mean,
                  reduce_image, return_both_maps)
 
