@@ -130,6 +130,22 @@ S2G_API int s2g_deposit_2d_dev(s2g_ctx* ctx, const void* pos, const void* hsml, 
                                double len2pix, int64_t nx, int64_t ny, int32_t kernel, int32_t calc_mean,
                                int32_t accumulate, double* image_dev);
 
+/* ---- Smac 2D deposit with a rotation measure per particle: replaces cic_mapping_2D(Pos,HSML,M,Rho,Bin_Q,Weights,RM;
+ *      param,kernel,calc_mean,stokes) for RM !== nothing (cic_2D.jl:103-111, branch :129-131 / :201-217, and
+ *      faraday_rotate_pixel! cic_shared.jl:129-159).  Particles are composited strictly in the order given (the
+ *      caller passes them far -> near, cic_interpolation.jl:74-83); planes 1/2 of the image are Stokes Q/U.
+ *      rm: n doubles (the reference's faraday_rotate_pixel! only accepts Float64).  stokes == 0 reproduces the
+ *      reference too: RM is then read but nothing rotates (which is also all sphMapping ever asks for, because it
+ *      does not forward `stokes`, cic_interpolation.jl:152-155). */
+S2G_API int s2g_deposit_2d_rm(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                              const void* binq, const void* w, const double* rm, int64_t n, int32_t n_images,
+                              int32_t in_dtype, double len2pix, int64_t nx, int64_t ny, int32_t kernel,
+                              int32_t calc_mean, int32_t stokes, double* image_out, s2g_stats* stats_or_null);
+S2G_API int s2g_deposit_2d_rm_dev(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                                  const void* binq, const void* w, const double* rm, int64_t n, int32_t n_images,
+                                  int32_t in_dtype, double len2pix, int64_t nx, int64_t ny, int32_t kernel,
+                                  int32_t calc_mean, int32_t stokes, double* image_dev);
+
 /* ---- Smac 3D deposit: replaces cic_mapping_3D (src/cic_interpolation/cic_3D.jl:110-209).
  *      image: n^3 x 2 doubles (quantity plane, weight plane). */
 S2G_API int s2g_deposit_3d(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
@@ -182,6 +198,25 @@ S2G_API int s2g_sphmap_dev(s2g_ctx* ctx, int32_t dims, const void* pos, const vo
                            int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
                            const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
                            int32_t accumulate, double* image_dev);
+/* ---- map_it's projection pre-step (cic_interpolation.jl:331-345) fused into the position load of the same call:
+ *      perm (3 ints, or NULL): new component d = old component perm[d]; {0,2,1} = rotate_to_xz_plane!,
+ *           {1,2,0} = rotate_to_yz_plane! (src/shared/rotate_particles.jl:35-73); exact, stays in the input precision.
+ *      rot  (9 doubles row-major, or NULL): new = rot * old in Float64 = rotate_3D (rotate_particles.jl:7-13).
+ *      shift/halfsize/len2pix describe the map in the ROTATED frame (rotate_to_xz_plane(par),
+ *      src/shared/rotate_parameters.jl:27-59).  The caller's positions are only read (map_it works on a copy). */
+S2G_API int s2g_sphmap_projected(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                                 const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                                 int32_t in_dtype, const int32_t* perm_or_null, const double* rot_or_null,
+                                 const double shift[3], int32_t periodic, double boxsize, const double halfsize[3],
+                                 double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
+                                 int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
+                                 s2g_stats* stats_or_null);
+S2G_API int s2g_sphmap_projected_dev(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                                     const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                                     int32_t in_dtype, const int32_t* perm_or_null, const double* rot_or_null,
+                                     const double shift[3], int32_t periodic, double boxsize,
+                                     const double halfsize[3], double len2pix, int64_t npix, int32_t kernel,
+                                     int32_t calc_mean, int32_t accumulate, double* image_dev);
 
 /* ---- HEALPix particle loop (src/healpix_interpolation/main.jl:143-213, pixel_weights.jl, constributing_pixels.jl).
  *      pos relative to the observer, already filtered (filter_sort_particles stays host logic).

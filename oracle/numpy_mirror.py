@@ -51,11 +51,23 @@ def _x_dx(x, h, i):
     return x - i - 0.5, min(x + h, i + 1) - max(x - h, i)
 
 
-def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel, kdim=2, calc_mean=True):
+def _jl_mod(x, y):
+    # Julia mod(x::Float64, y::Float64): rem, then move into the sign of y
+    r = math.fmod(x, y)
+    if r == 0:
+        return math.copysign(r, y)
+    if (r > 0) != (y > 0):
+        return r + y
+    return r
+
+
+def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel, kdim=2, calc_mean=True, rm=None, stokes=False):
+    """rm/stokes: the Faraday-rotation branch of cic_2D.jl:201-217 + cic_shared.jl:129-159."""
     pos = np.asarray(pos, float); binq = np.asarray(binq, float)
     n = len(hsml)
     nim = 1 if binq.ndim == 1 else binq.shape[1]
     img = np.zeros((npix * npix, nim + 1))
+    touched = set()
     for p in range(n):
         bq = np.atleast_1d(binq[p])
         allzero = bool(np.all(bq == 0))
@@ -104,7 +116,16 @@ def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel, kdim=2, ca
         an = kn * wpp * w[p] * dz
         for idx in wk:
             pw = wk[idx] * A[idx] * an
+            if rm is not None and idx in touched and stokes:
+                ang = _jl_mod(rm[p] * pw, math.pi)
+                Q, U = img[idx, 0], img[idx, 1]
+                ip = math.sqrt(Q * Q + U * U)
+                with np.errstate(all="ignore"):
+                    psi = 0.5 * math.atan(np.float64(U) / np.float64(Q))
+                img[idx, 0] = ip * math.cos(2 * (psi + ang))
+                img[idx, 1] = ip * math.sin(2 * (psi + ang))
             if pw != 0.0:
+                touched.add(idx)
                 img[idx, nim] += pw
                 if allzero:
                     img[idx, 0] += 0.0 * pw

@@ -61,6 +61,9 @@ def lib():
         L.s2go_filter_particles_f64.argtypes = [_dp, C.c_int64, _dp, _dp, _bp]
         L.s2go_filter_particles_f32.argtypes = [_fp, C.c_int64, _dp, _dp, _bp]
         L.s2go_domain_decomposition.argtypes = [C.c_int64, C.c_int64, _ip, _ip]
+        L.s2go_cic_mapping_2d_rm.restype = C.c_int
+        L.s2go_cic_mapping_2d_rm.argtypes = [_dp] * 7 + [C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int,
+                                                         C.c_int, C.c_int, _dp, _ip]
         L.s2go_cic_mapping_2d.restype = C.c_int
         L.s2go_cic_mapping_2d.argtypes = [_dp] * 6 + [C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int,
                                                       C.c_int, _dp, _ip, _ip]
@@ -217,6 +220,25 @@ def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel="WendlandC6
     return (image, fp, stats) if want_footprints else (image, stats)
 
 
+def cic_mapping_2d_rm(pos, hsml, m, rho, binq, w, rm, len2pix, npix, kernel="WendlandC6", kernel_dim=2,
+                      calc_mean=True, stokes=True):
+    """cic_mapping_2D with the RM argument (cic_2D.jl:103-244 + faraday_rotate_pixel! cic_shared.jl:129-159):
+    particles are composited in the given order; planes 1/2 are Stokes Q/U."""
+    pos = _c64(pos); hsml = _c64(hsml); m = _c64(m); rho = _c64(rho); w = _c64(w); rm = _c64(rm)
+    binq = _c64(binq)
+    n = hsml.shape[0]
+    n_images = 1 if binq.ndim == 1 else binq.shape[1]
+    image = np.zeros((npix * npix, n_images + 1), order="F")
+    st = np.zeros(4, dtype=np.int64)
+    rc = lib().s2go_cic_mapping_2d_rm(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), _d(rm), n, n_images,
+                                      float(len2pix), int(npix), KERNEL_IDS[kernel], kernel_dim, int(calc_mean),
+                                      int(stokes), _d(image), _i(st))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    stats = dict(n_mapped=int(st[0]), footprint_pixels=int(st[1]), touched_pixels=int(st[2]), n_fallback=int(st[3]))
+    return image, stats
+
+
 def cic_mapping_3d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel="Cubic", kernel_dim=3, calc_mean=False,
                    want_footprints=False, n_workers=0):
     pos = _c64(pos); hsml = _c64(hsml); m = _c64(m); rho = _c64(rho); w = _c64(w); binq = _c64(binq)
@@ -260,10 +282,13 @@ def reduce_image_3d(image, npix, reduce_image=True):
 
 def sph_mapping(pos, hsml, m, rho, binq, weights=None, *, param: MappingParameters, kernel="WendlandC6",
                 kernel_dim=None, parallel=False, n_workers=0, reduce_image=True, return_both_maps=False,
-                dimensions=2, calc_mean=False, sort_z=False):
+                dimensions=2, calc_mean=False, sort_z=False, stokes=False, rm=None):
     """cic_interpolation.jl:35-273.  pos is (N,3) [Julia (3,N)] and IS MUTATED (Q1)."""
     if weights is None:
         weights = rho
+    if stokes:  # cic_interpolation.jl:74-81: back-to-front order, serial
+        sort_z = True
+        parallel = False
     pos = _pos3xn(pos)
     if not pos.flags.c_contiguous or pos.dtype not in (np.float32, np.float64):
         raise ValueError("pos must be C-contiguous (N,3) float32/float64 (it is recentred in place)")
@@ -278,7 +303,16 @@ def sph_mapping(pos, hsml, m, rho, binq, weights=None, *, param: MappingParamete
     nw = n_workers if parallel else 0
     if dimensions == 2:
         kd = 2 if kernel_dim is None else kernel_dim
-        image, _ = cic_mapping_2d(x, hs, mm, rr, bq, ww, par.len2pix, npix, kernel, kd, calc_mean, n_workers=nw)
+        if rm is not None:
+            if parallel:
+                raise ValueError("the reference passes RM to the serial deposit only (cic_interpolation.jl:152)")
+            # NB: sphMapping does NOT forward `stokes` to cic_mapping_2D (cic_interpolation.jl:152-155), so the
+            # rotation branch of faraday_rotate_pixel! is dead through the public API; only a direct
+            # cic_mapping_2D(...; stokes=true) call rotates.  Mirrored literally.
+            image, _ = cic_mapping_2d_rm(x, hs, mm, rr, bq, ww, np.asarray(rm)[sel], par.len2pix, npix, kernel, kd,
+                                         calc_mean, False)
+        else:
+            image, _ = cic_mapping_2d(x, hs, mm, rr, bq, ww, par.len2pix, npix, kernel, kd, calc_mean, n_workers=nw)
         if return_both_maps:
             return image
         return reduce_image_2d(image, int(param.Npixels[0]), int(param.Npixels[1]), reduce_image)
@@ -288,6 +322,68 @@ def sph_mapping(pos, hsml, m, rho, binq, weights=None, *, param: MappingParamete
         image, _ = cic_mapping_3d(x, hs, mm, rr, bq, ww, par.len2pix, npix, kernel, kd, False, n_workers=nw)
         return reduce_image_3d(image, npix, reduce_image)
     raise ValueError("dimensions must be 2 or 3")
+
+
+# --------------------------------------------------------------------------- projections (map_it pre-step)
+def rotate_to_xz_plane(pos):
+    """rotate_to_xz_plane! (rotate_particles.jl:35-43): swaps y and z of every particle, in place.  pos (N,3)."""
+    for i in range(pos.shape[0]):
+        pos3 = pos[i, 1].copy()
+        pos[i, 1] = pos[i, 2]
+        pos[i, 2] = pos3
+    return pos
+
+
+def rotate_to_yz_plane(pos):
+    """rotate_to_yz_plane! (rotate_particles.jl:65-74): (x,y,z) <- (y,z,x), in place."""
+    for i in range(pos.shape[0]):
+        pos3 = pos[i, 0].copy()
+        pos[i, 0] = pos[i, 1]
+        pos[i, 1] = pos[i, 2]
+        pos[i, 2] = pos3
+    return pos
+
+
+def rotate_parameters_xz(par: MappingParameters):
+    """rotate_to_xz_plane(par) (rotate_parameters.jl:27-40)"""
+    return mapping_parameters(center=[par.center[0], par.center[2], par.center[1]], x_lim=par.x_lim.copy(),
+                              y_lim=par.z_lim.copy(), z_lim=par.y_lim.copy(), Npixels=int(par.Npixels.max()),
+                              boxsize=par.boxsize)
+
+
+def rotate_parameters_yz(par: MappingParameters):
+    """rotate_to_yz_plane(par) (rotate_parameters.jl:48-59)"""
+    return mapping_parameters(center=[par.center[1], par.center[2], par.center[0]], x_lim=par.y_lim.copy(),
+                              y_lim=par.z_lim.copy(), z_lim=par.x_lim.copy(), Npixels=int(par.Npixels.max()),
+                              boxsize=par.boxsize)
+
+
+def rotate_3d(pos, alpha, beta, gamma):
+    """rotate_3D (rotate_particles.jl:7-13): RotXYZ(deg2rad.(angles)) * x, with RotXYZ = Rx*Ry*Rz built here from the
+    three elementary matrices (Rotations.jl itself is not in the reference tree: last-ulp parity unpinned)."""
+    import math
+    a, b, g = math.radians(alpha), math.radians(beta), math.radians(gamma)
+    rx = np.array([[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]])
+    ry = np.array([[math.cos(b), 0, math.sin(b)], [0, 1, 0], [-math.sin(b), 0, math.cos(b)]])
+    rz = np.array([[math.cos(g), -math.sin(g), 0], [math.sin(g), math.cos(g), 0], [0, 0, 1]])
+    rot = rx @ ry @ rz
+    return (rot @ np.asarray(pos, dtype=np.float64).T).T.copy()
+
+
+def map_it(pos_in, hsml, m, rho, binq, weights, *, param: MappingParameters, kernel="WendlandC6", reduce_image=True,
+           calc_mean=True, projection="xy", **kw):
+    """map_it without the FITS output (cic_interpolation.jl:312-359)."""
+    pos = np.array(pos_in, copy=True)
+    if projection == "xy":
+        par = param
+    elif projection == "xz":
+        pos = rotate_to_xz_plane(pos); par = rotate_parameters_xz(param)
+    elif projection == "yz":
+        pos = rotate_to_yz_plane(pos); par = rotate_parameters_yz(param)
+    else:
+        pos = rotate_3d(pos, *projection); par = param  # (`par` is unassigned in the reference: intent restated)
+    return sph_mapping(np.ascontiguousarray(pos), hsml, m, rho, binq, weights, param=par, kernel=kernel,
+                       reduce_image=reduce_image, calc_mean=calc_mean, **kw)
 
 
 # --------------------------------------------------------------------------- HEALPix

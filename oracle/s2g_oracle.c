@@ -287,10 +287,38 @@ typedef struct {
     int64_t n_mapped, footprint_pixels, touched_pixels, n_fallback;
 } s2go_stats;
 
+/* faraday_rotate_pixel! (cic_shared.jl:129-159).  image[idx,1] = Stokes Q, image[idx,2] = Stokes U (plane 2 is the
+ * weight plane when only one quantity is mapped -- the reference does not check).  mod(x, pi) is Julia's
+ * floating-point mod: r = rem(x, y) (exact, fmod); r == 0 -> copysign(r, y); sign(r) != sign(y) -> r + y.
+ * psi = 0.5*atan(U/Q) is the ONE-argument arctangent (the quadrant of (Q,U) is lost: a pixel with Q < 0 comes back
+ * with both signs flipped even for a zero rotation; Q = U = 0 gives NaN).  Reproduced as is. */
+static inline double julia_mod_pi(double x)
+{
+    const double y = 3.141592653589793; /* Float64(pi) */
+    double r = fmod(x, y);
+    if (r == 0.0) return copysign(r, y);
+    if ((r > 0.0) != (y > 0.0)) return r + y;
+    return r;
+}
+static inline void faraday_rotate_pixel(double* image, int64_t idx, int64_t N_distr, double pRM, double pix_weight,
+                                        int stokes)
+{
+    double _RM = pRM * pix_weight;
+    _RM = julia_mod_pi(_RM);
+    if (stokes) {
+        double Q = image[idx], U = image[idx + N_distr];
+        double Ipol = sqrt(Q * Q + U * U);
+        double psi = 0.5 * atan(U / Q);
+        image[idx] = Ipol * cos(2.0 * (psi + _RM));
+        image[idx + N_distr] = Ipol * sin(2.0 * (psi + _RM));
+    }
+}
+
 static void cic_mapping_2d_range(const double* pos, const double* hsml, const double* m, const double* rho,
                                  const double* binq, const double* w, int64_t p0, int64_t p1, int n_images,
                                  double len2pix, int64_t npix, int kid, int kdim, int calc_mean, double* image,
-                                 double* wk, double* A, int64_t* fp, s2go_stats* st)
+                                 double* wk, double* A, int64_t* fp, s2go_stats* st, const double* rm, int stokes,
+                                 uint8_t* touched_pixel)
 {
     const int64_t N_distr = npix * npix;
     for (int64_t p = p0; p < p1; p++) {
@@ -369,7 +397,10 @@ static void cic_mapping_2d_range(const double* pos, const double* hsml, const do
             for (int64_t j = jMin; j <= jMax; j++) {
                 int64_t idx = s2go_calculate_index_2d(i, j, npix);
                 double pix_weight = wk[idx] * A[idx] * area_norm;
+                /* cic_2D.jl:201-209: Faraday-rotate what the pixel holds so far (only if something was deposited) */
+                if (rm && touched_pixel[idx]) faraday_rotate_pixel(image, idx, N_distr, rm[p], pix_weight, stokes);
                 if (pix_weight != 0.0) {
+                    if (rm) touched_pixel[idx] = 1; /* cic_2D.jl:214-217 */
                     image[idx + N_distr * n_images] += pix_weight;
                     if (all_zero) /* bin_q collapsed to scalar 0.0 (cic_2D.jl:160-162) */
                         image[idx] += 0.0 * pix_weight;
@@ -393,9 +424,29 @@ S2GO_API int s2go_cic_mapping_2d(const double* pos, const double* hsml, const do
     if (!wk || !A) { free(wk); free(A); return -1; }
     s2go_stats st = {0, 0, 0, 0};
     cic_mapping_2d_range(pos, hsml, m, rho, binq, w, 0, n, n_images, len2pix, npix, kid, kdim, calc_mean, image, wk, A,
-                         fp, &st);
+                         fp, &st, NULL, 0, NULL);
     if (stats4) { stats4[0] = st.n_mapped; stats4[1] = st.footprint_pixels; stats4[2] = st.touched_pixels; stats4[3] = st.n_fallback; }
     free(wk); free(A);
+    return 0;
+}
+
+/* cic_mapping_2D with the RM argument (cic_2D.jl:103-244, RM !== nothing): particles are processed strictly in the
+ * given order (the caller sorted them far -> near, cic_interpolation.jl:74-83); serial by construction. */
+S2GO_API int s2go_cic_mapping_2d_rm(const double* pos, const double* hsml, const double* m, const double* rho,
+                                    const double* binq, const double* w, const double* rm, int64_t n, int n_images,
+                                    double len2pix, int64_t npix, int kid, int kdim, int calc_mean, int stokes,
+                                    double* image, int64_t* stats4)
+{
+    const int64_t N_distr = npix * npix;
+    double* wk = (double*)calloc((size_t)N_distr, sizeof(double));
+    double* A = (double*)malloc((size_t)N_distr * sizeof(double));
+    uint8_t* touched = (uint8_t*)calloc((size_t)N_distr, 1);
+    if (!wk || !A || !touched) { free(wk); free(A); free(touched); return -1; }
+    s2go_stats st = {0, 0, 0, 0};
+    cic_mapping_2d_range(pos, hsml, m, rho, binq, w, 0, n, n_images, len2pix, npix, kid, kdim, calc_mean, image, wk, A,
+                         NULL, &st, rm, stokes, touched);
+    if (stats4) { stats4[0] = st.n_mapped; stats4[1] = st.footprint_pixels; stats4[2] = st.touched_pixels; stats4[3] = st.n_fallback; }
+    free(wk); free(A); free(touched);
     return 0;
 }
 
@@ -531,7 +582,7 @@ S2GO_API int s2go_cic_mapping_parallel(int dims, const double* pos, const double
             fail = 1;
         } else if (dims == 2)
             cic_mapping_2d_range(pos, hsml, m, rho, binq, w, start[t], end[t], n_images, len2pix, npix, kid, kdim,
-                                 calc_mean, img, wk, A, NULL, NULL);
+                                 calc_mean, img, wk, A, NULL, NULL, NULL, 0, NULL);
         else
             cic_mapping_3d_range(pos, hsml, m, rho, binq, w, start[t], end[t], len2pix, npix, kid, kdim, calc_mean, img,
                                  wk, A, NULL, NULL, NULL);

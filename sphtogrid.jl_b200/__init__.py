@@ -12,6 +12,8 @@ from .mapping import (sphMapping, map_it, cic_mapping_2D, cic_mapping_3D, reduce
                       part_weight_one, part_weight_physical, part_weight_emission, part_weight_spectroscopic)
 from .healpix import healpix_map, healpix_deposit, filter_sort_particles, find_in_shell  # noqa: F401
 from .stencils import cic_deposit, tsc_deposit  # noqa: F401
+from .rotate import (rotate_3D, rotate_3D_, rotate_to_xz_plane, rotate_to_yz_plane,  # noqa: F401
+                     project_along_axis, euler_matrix)
 from . import distributed, io  # noqa: F401
 from .distributed import distributed_cic_map, distributed_allsky_map  # noqa: F401
 from .io import write_fits_image, read_fits_image  # noqa: F401

@@ -73,6 +73,10 @@ _SIGS = {
     "s2g_deposit_2d": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i32, _f64, _i64, _i64, _i32, _i32, _vp,
                                                     C.POINTER(Stats)]),
     "s2g_deposit_2d_dev": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i32, _f64, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "s2g_deposit_2d_rm": (C.c_int, [_vp] + [_vp] * 7 + [_i64, _i32, _i32, _f64, _i64, _i64, _i32, _i32, _i32, _vp,
+                                                       C.POINTER(Stats)]),
+    "s2g_deposit_2d_rm_dev": (C.c_int, [_vp] + [_vp] * 7 + [_i64, _i32, _i32, _f64, _i64, _i64, _i32, _i32, _i32,
+                                                           _vp]),
     "s2g_deposit_3d": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _f64, _i64, _i32, _i32, _vp, C.POINTER(Stats)]),
     "s2g_deposit_3d_dev": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _f64, _i64, _i32, _i32, _i32, _vp]),
     "s2g_footprints": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _vp]),
@@ -85,6 +89,12 @@ _SIGS = {
                                                       _i32, _i32, _vp, _vp, C.POINTER(Stats)]),
     "s2g_sphmap_dev": (C.c_int, [_vp, _i32] + [_vp] * 6 + [_i64, _i32, _i32, _dp, _i32, _f64, _dp, _f64, _i64, _i32,
                                                           _i32, _i32, _vp]),
+    "s2g_sphmap_projected": (C.c_int, [_vp, _i32] + [_vp] * 6 + [_i64, _i32, _i32, C.POINTER(C.c_int32), _dp, _dp, _i32,
+                                                                _f64, _dp, _f64, _i64, _i32, _i32, _i32, _i32, _vp, _vp,
+                                                                C.POINTER(Stats)]),
+    "s2g_sphmap_projected_dev": (C.c_int, [_vp, _i32] + [_vp] * 6 + [_i64, _i32, _i32, C.POINTER(C.c_int32), _dp, _dp,
+                                                                    _i32, _f64, _dp, _f64, _i64, _i32, _i32, _i32,
+                                                                    _vp]),
     "s2g_healpix_deposit": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i64, _i32, _i32, _vp, _vp, C.POINTER(Stats)]),
     "s2g_healpix_deposit_dev": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     "s2g_healpix_map": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _dp, _dp, _i64, _i32, _i32, _vp, _vp, _vp, C.POINTER(Stats)]),

@@ -423,6 +423,66 @@ extern "C" int s2g_deposit_2d(s2g_ctx* ctx, const void* pos, const void* hsml, c
     return S2G_OK;
 }
 
+// cic_mapping_2D with RM (cic_2D.jl:201-217): stokes == 0 -> RM is inert (faraday_rotate_pixel! does nothing), the
+// ordinary deposit gives the reference result; stokes != 0 -> ordered compositing (s2g_stokes2d.cu)
+extern "C" int s2g_deposit_2d_rm_dev(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                                     const void* binq, const void* w, const double* rm, int64_t n, int32_t n_images,
+                                     int32_t in_dtype, double len2pix, int64_t nx, int64_t ny, int32_t kernel,
+                                     int32_t calc_mean, int32_t stokes, double* image_dev)
+{
+    CTX_ENTER(ctx);
+    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, nx, kernel));
+    S2G_CHECK(nx == ny, S2G_EINVAL, "%s: nx must equal ny", __func__);
+    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", __func__);
+    S2G_CHECK(image_dev != nullptr, S2G_EINVAL, "%s: image is NULL", __func__);
+    S2G_CHECK(rm != nullptr || n == 0, S2G_EINVAL, "%s: rm is NULL", __func__);
+    S2G_TRY(stats_begin(ctx, n));
+    S2G_CUDA(cudaMemsetAsync(image_dev, 0, sizeof(double) * (size_t)(nx * ny) * (size_t)(n_images + 1), ctx->stream));
+    s2g_particles P = dev_particles(pos, hsml, m, rho, binq, w, n, in_dtype);
+    s2g_geom G = make_geom(len2pix, nx, n_images, calc_mean);
+    if (!stokes) return s2g_launch_deposit_2d(ctx, P, G, kernel, image_dev);
+    return s2g_launch_stokes_2d(ctx, P, G, kernel, rm, image_dev);
+}
+
+extern "C" int s2g_deposit_2d_rm(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                                 const void* binq, const void* w, const double* rm, int64_t n, int32_t n_images,
+                                 int32_t in_dtype, double len2pix, int64_t nx, int64_t ny, int32_t kernel,
+                                 int32_t calc_mean, int32_t stokes, double* image_out, s2g_stats* stats)
+{
+    CTX_ENTER(ctx);
+    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, nx, kernel));
+    S2G_CHECK(nx == ny, S2G_EINVAL, "%s: nx must equal ny", __func__);
+    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", __func__);
+    S2G_CHECK(image_out != nullptr, S2G_EINVAL, "%s: image_out is NULL", __func__);
+    S2G_CHECK(rm != nullptr || n == 0, S2G_EINVAL, "%s: rm is NULL", __func__);
+    S2G_TRY(stats_begin(ctx, n));
+    const size_t img_bytes = sizeof(double) * (size_t)(nx * ny) * (size_t)(n_images + 1);
+    void *dimg, *drm;
+    S2G_TRY(s2g_scratch(ctx, "image", img_bytes, &dimg));
+    S2G_TRY(s2g_scratch(ctx, "in_rm", sizeof(double) * (size_t)(n > 0 ? n : 1), &drm));
+    S2G_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    s2g_particles P;
+    S2G_TRY(stage_particles(ctx, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, P));
+    if (n > 0) S2G_CUDA(cudaMemcpyAsync(drm, rm, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    S2G_CUDA(cudaMemsetAsync(dimg, 0, img_bytes, ctx->stream));
+    S2G_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    s2g_geom G = make_geom(len2pix, nx, n_images, calc_mean);
+    if (!stokes)
+        S2G_TRY(s2g_launch_deposit_2d(ctx, P, G, kernel, (double*)dimg));
+    else
+        S2G_TRY(s2g_launch_stokes_2d(ctx, P, G, kernel, (const double*)drm, (double*)dimg));
+    S2G_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    S2G_CUDA(cudaMemcpyAsync(image_out, dimg, img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    S2G_TRY(stats_collect(ctx));
+    ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_compute = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_d2h = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
+    if (stats) *stats = ctx->stats;
+    return S2G_OK;
+}
+
 extern "C" int s2g_deposit_3d_dev(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
                                   const void* binq, const void* w, int64_t n, int32_t in_dtype, double len2pix,
                                   int64_t npix, int32_t kernel, int32_t calc_mean, int32_t accumulate,
@@ -581,45 +641,90 @@ extern "C" int s2g_center_filter(s2g_ctx* ctx, const void* pos, int64_t n, int32
 // ------------------------------------------------------------------------------------------------
 // fused sphMapping body
 // ------------------------------------------------------------------------------------------------
-extern "C" int s2g_sphmap_dev(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
-                              const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
-                              int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
-                              const double halfsize[3], double len2pix, int64_t npix, int32_t kernel,
-                              int32_t calc_mean, int32_t accumulate, double* image_dev)
+// projection of map_it (cic_interpolation.jl:331-345) fused into the position load: an axis permutation
+// (rotate_to_xz_plane! / rotate_to_yz_plane!, rotate_particles.jl:35-73) or a 3x3 matrix (rotate_3D, :7-13)
+static int set_projection(const char* fn, s2g_particles& P, const int32_t* perm, const double* rot)
 {
-    CTX_ENTER(ctx);
-    S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", __func__);
-    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, npix, kernel));
-    S2G_CHECK(shift && halfsize && image_dev, S2G_EINVAL, "%s: NULL argument", __func__);
-    S2G_CHECK(dims == 2 || n_images == 1, S2G_EINVAL, "%s: 3D maps take a single quantity", __func__);
-    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", __func__);
-    S2G_CHECK(dims == 2 || npix <= 2048, S2G_EINVAL, "%s: npix > 2048 not supported in 3D", __func__);
+    S2G_CHECK(!(perm && rot), S2G_EINVAL, "%s: give either an axis permutation or a rotation matrix, not both", fn);
+    if (perm) {
+        int seen = 0;
+        for (int d = 0; d < 3; ++d) {
+            S2G_CHECK(perm[d] >= 0 && perm[d] <= 2, S2G_EINVAL, "%s: perm[%d] = %d is not an axis", fn, d, perm[d]);
+            seen |= 1 << perm[d];
+            P.perm[d] = perm[d];
+        }
+        S2G_CHECK(seen == 7, S2G_EINVAL, "%s: perm is not a permutation of (0,1,2)", fn);
+        P.proj = (perm[0] == 0 && perm[1] == 1 && perm[2] == 2) ? 0 : 1;
+    } else if (rot) {
+        for (int k = 0; k < 9; ++k) P.rot[k] = rot[k];
+        P.proj = 2;
+    }
+    return S2G_OK;
+}
+
+static int sphmap_dev_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                           const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                           int32_t in_dtype, const int32_t* perm, const double* rot, const double shift[3],
+                           int32_t periodic, double boxsize, const double halfsize[3], double len2pix, int64_t npix,
+                           int32_t kernel, int32_t calc_mean, int32_t accumulate, double* image_dev)
+{
+    S2G_CHECK(ctx != nullptr, S2G_EINVAL, "%s: ctx is NULL", fn);
+    S2G_CUDA(cudaSetDevice(ctx->device));
+    S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", fn);
+    S2G_TRY(check_common(fn, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, npix, kernel));
+    S2G_CHECK(shift && halfsize && image_dev, S2G_EINVAL, "%s: NULL argument", fn);
+    S2G_CHECK(dims == 2 || n_images == 1, S2G_EINVAL, "%s: 3D maps take a single quantity", fn);
+    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", fn);
+    S2G_CHECK(dims == 2 || npix <= 2048, S2G_EINVAL, "%s: npix > 2048 not supported in 3D", fn);
     S2G_TRY(stats_begin(ctx, n));
     const size_t ncell = dims == 2 ? (size_t)(npix * npix) : (size_t)(npix * npix * npix);
     const int planes = dims == 2 ? n_images + 1 : 2;
     if (!accumulate) S2G_CUDA(cudaMemsetAsync(image_dev, 0, sizeof(double) * ncell * planes, ctx->stream));
     s2g_particles P = dev_particles(pos, hsml, m, rho, binq, w, n, in_dtype);
     set_center(P, shift, periodic, boxsize, halfsize);
+    S2G_TRY(set_projection(fn, P, perm, rot));
     // the reference does not forward calc_mean to cic_mapping_3D (cic_interpolation.jl:219-221): default false
     s2g_geom G = make_geom(len2pix, npix, dims == 2 ? n_images : 1, dims == 2 ? calc_mean : 0);
     if (dims == 2) return s2g_launch_deposit_2d(ctx, P, G, kernel, image_dev);
     return s2g_launch_deposit_3d(ctx, P, G, kernel, image_dev);
 }
 
-extern "C" int s2g_sphmap(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
-                          const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
-                          int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
-                          const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
-                          int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
-                          s2g_stats* stats)
+extern "C" int s2g_sphmap_dev(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                              const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                              int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
+                              const double halfsize[3], double len2pix, int64_t npix, int32_t kernel,
+                              int32_t calc_mean, int32_t accumulate, double* image_dev)
 {
-    CTX_ENTER(ctx);
-    S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", __func__);
-    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, npix, kernel));
-    S2G_CHECK(shift && halfsize && out, S2G_EINVAL, "%s: NULL argument", __func__);
-    S2G_CHECK(dims == 2 || n_images == 1, S2G_EINVAL, "%s: 3D maps take a single quantity", __func__);
-    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", __func__);
-    S2G_CHECK(dims == 2 || npix <= 2048, S2G_EINVAL, "%s: npix > 2048 not supported in 3D", __func__);
+    return sphmap_dev_impl(__func__, ctx, dims, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, nullptr, nullptr,
+                           shift, periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, accumulate, image_dev);
+}
+
+extern "C" int s2g_sphmap_projected_dev(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                                        const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                                        int32_t in_dtype, const int32_t* perm, const double* rot,
+                                        const double shift[3], int32_t periodic, double boxsize,
+                                        const double halfsize[3], double len2pix, int64_t npix, int32_t kernel,
+                                        int32_t calc_mean, int32_t accumulate, double* image_dev)
+{
+    return sphmap_dev_impl(__func__, ctx, dims, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, perm, rot, shift,
+                           periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, accumulate, image_dev);
+}
+
+static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                       const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images, int32_t in_dtype,
+                       const int32_t* perm, const double* rot, const double shift[3], int32_t periodic, double boxsize,
+                       const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
+                       int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
+                       s2g_stats* stats)
+{
+    S2G_CHECK(ctx != nullptr, S2G_EINVAL, "%s: ctx is NULL", fn);
+    S2G_CUDA(cudaSetDevice(ctx->device));
+    S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", fn);
+    S2G_TRY(check_common(fn, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, npix, kernel));
+    S2G_CHECK(shift && halfsize && out, S2G_EINVAL, "%s: NULL argument", fn);
+    S2G_CHECK(dims == 2 || n_images == 1, S2G_EINVAL, "%s: 3D maps take a single quantity", fn);
+    S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", fn);
+    S2G_CHECK(dims == 2 || npix <= 2048, S2G_EINVAL, "%s: npix > 2048 not supported in 3D", fn);
     S2G_TRY(stats_begin(ctx, n));
     const size_t ncell = dims == 2 ? (size_t)(npix * npix) : (size_t)(npix * npix * npix);
     const int planes = dims == 2 ? n_images + 1 : 2;
@@ -634,6 +739,9 @@ extern "C" int s2g_sphmap(s2g_ctx* ctx, int32_t dims, const void* pos, const voi
     S2G_CUDA(cudaMemsetAsync(dimg, 0, sizeof(double) * ncell * planes, ctx->stream));
     S2G_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     set_center(P, shift, periodic, boxsize, halfsize);
+    S2G_TRY(set_projection(fn, P, perm, rot));
+    S2G_CHECK(!(P.proj == 2 && pos_recentred_out && in_dtype == S2G_F32), S2G_EINVAL,
+              "%s: rotated Float32 positions are Float64 in the reference; pos_recentred_out is not available", fn);
     s2g_geom G = make_geom(len2pix, npix, dims == 2 ? n_images : 1, dims == 2 ? calc_mean : 0);
     if (dims == 2)
         S2G_TRY(s2g_launch_deposit_2d(ctx, P, G, kernel, (double*)dimg));
@@ -667,6 +775,30 @@ extern "C" int s2g_sphmap(s2g_ctx* ctx, int32_t dims, const void* pos, const voi
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[4]);
     if (stats) *stats = ctx->stats;
     return S2G_OK;
+}
+
+extern "C" int s2g_sphmap(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                          const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                          int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
+                          const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
+                          int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
+                          s2g_stats* stats)
+{
+    return sphmap_impl(__func__, ctx, dims, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, nullptr, nullptr, shift,
+                       periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, reduce_image, return_both_maps,
+                       pos_recentred_out, out, stats);
+}
+
+extern "C" int s2g_sphmap_projected(s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                                    const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                                    int32_t in_dtype, const int32_t* perm, const double* rot, const double shift[3],
+                                    int32_t periodic, double boxsize, const double halfsize[3], double len2pix,
+                                    int64_t npix, int32_t kernel, int32_t calc_mean, int32_t reduce_image,
+                                    int32_t return_both_maps, void* pos_recentred_out, double* out, s2g_stats* stats)
+{
+    return sphmap_impl(__func__, ctx, dims, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, perm, rot, shift,
+                       periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, reduce_image, return_both_maps,
+                       pos_recentred_out, out, stats);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -115,6 +115,12 @@ struct s2g_particles {
     double shift[3];
     double boxsize;
     double halfsize[3];
+    // optional projection applied BEFORE the recentring (map_it, cic_interpolation.jl:331-345):
+    //   proj == 1: axis permutation, new component d = old component perm[d]   (rotate_to_xz/yz_plane!)
+    //   proj == 2: 3x3 matrix, new = rot * old in Float64                      (rotate_3D, rot row-major)
+    int proj;
+    int perm[3];
+    double rot[9];
 };
 
 #ifdef __CUDACC__
@@ -137,8 +143,31 @@ __device__ __forceinline__ double ld_in(const void* p, long long i, int dtype)
 // the subtraction is evaluated in Float64 and ROUNDED BACK to the storage type (Float32 stays Float32).
 __device__ __forceinline__ double ld_pos(const s2g_particles& P, long long p, int d)
 {
+    if (P.proj == 2) {
+        // rotate_3D (rotate_particles.jl:7-13): rot * x is a Float64 matrix whatever the storage type of x was, so
+        // the recentring that follows happens in Float64.  Row times column, left to right, no contraction.
+        double x0, x1, x2;
+        if (P.in_dtype == S2G_F64) {
+            const double* q = reinterpret_cast<const double*>(P.pos) + 3 * p;
+            x0 = __ldg(q); x1 = __ldg(q + 1); x2 = __ldg(q + 2);
+        } else {
+            const float* q = reinterpret_cast<const float*>(P.pos) + 3 * p;
+            x0 = (double)__ldg(q); x1 = (double)__ldg(q + 1); x2 = (double)__ldg(q + 2);
+        }
+        double v = __dadd_rn(__dadd_rn(__dmul_rn(P.rot[3 * d], x0), __dmul_rn(P.rot[3 * d + 1], x1)),
+                             __dmul_rn(P.rot[3 * d + 2], x2));
+        if (P.fuse_center) {
+            v = __dadd_rn(v, -P.shift[d]);
+            if (P.periodic) {
+                double hb = P.boxsize / 2;
+                if (fabs(v) > hb) v = v > 0 ? __dadd_rn(v, -hb) : __dadd_rn(v, hb);
+            }
+        }
+        return v;
+    }
+    const int c = P.proj == 1 ? P.perm[d] : d;
     if (P.in_dtype == S2G_F64) {
-        double v = __ldg(reinterpret_cast<const double*>(P.pos) + 3 * p + d);
+        double v = __ldg(reinterpret_cast<const double*>(P.pos) + 3 * p + c);
         if (P.fuse_center) {
             v = __dadd_rn(v, -P.shift[d]);
             if (P.periodic) {
@@ -148,7 +177,7 @@ __device__ __forceinline__ double ld_pos(const s2g_particles& P, long long p, in
         }
         return v;
     } else {
-        float f = __ldg(reinterpret_cast<const float*>(P.pos) + 3 * p + d);
+        float f = __ldg(reinterpret_cast<const float*>(P.pos) + 3 * p + c);
         if (P.fuse_center) {
             f = __double2float_rn(__dadd_rn((double)f, -P.shift[d]));
             if (P.periodic) {
@@ -222,6 +251,8 @@ __device__ __forceinline__ void red_add(double* addr, double v)
 // internal launchers (defined in the per-path .cu files)
 // ------------------------------------------------------------------------------------------------
 int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image_dev);
+int s2g_launch_stokes_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const double* rm_dev,
+                         double* image_dev);
 int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image_dev);
 int s2g_launch_footprints(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int dims, long long* bounds_dev);
 int s2g_launch_reduce_2d(s2g_ctx* ctx, const double* image_dev, long long nx, long long ny, int n_images,

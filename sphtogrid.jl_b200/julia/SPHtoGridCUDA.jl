@@ -70,12 +70,25 @@ Drop-in for src/cic_interpolation/cic_2D.jl:103-244.  Returns `Matrix{Float64}(N
 function cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=nothing;
                         param, kernel::AbstractSPHKernel, show_progress::Bool=false,
                         calc_mean::Bool=true, stokes::Bool=false, ctx::Context=default_context())
-    (!isnothing(RM) || stokes) && error("RM / stokes mapping is not supported by libsphtogrid_cuda (S2G_EUNSUPPORTED)")
     T, pos, hsml, m, rho, bq, w = _uniform(Pos, HSML, M, Rho, Bin_Q, Weights)
     N = length(m)
     n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
     nx, ny = param.Npixels[1], param.Npixels[2]
     image = Matrix{Float64}(undef, nx * ny, n_images + 1)
+    if !isnothing(RM)
+        # Faraday-rotation branch (cic_2D.jl:201-217, cic_shared.jl:129-159): ordered compositing on the device;
+        # stokes=false leaves RM inert exactly like faraday_rotate_pixel! does
+        rm = RM::Vector{Float64}
+        GC.@preserve pos hsml m rho bq w rm image begin
+            check(ccall((:s2g_deposit_2d_rm, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                         Ptr{Float64}, Int64, Int32, Int32, Float64, Int64, Int64, Int32, Int32, Int32, Ptr{Float64},
+                         Ptr{Cvoid}),
+                        ctx.handle, pos, hsml, m, rho, bq, w, rm, N, n_images, T == Float32 ? S2G_F32 : S2G_F64,
+                        Float64(param.len2pix), nx, ny, kernel_id(kernel), calc_mean, stokes, image, C_NULL))
+        end
+        return image
+    end
     GC.@preserve pos hsml m rho bq w image begin
         check(ccall((:s2g_deposit_2d, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
@@ -209,6 +222,49 @@ function sphmap_fused(Pos::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; param, par_c
                     kernel_id(kernel), calc_mean, reduce_image, return_both_maps, pos_out, out, C_NULL))
     end
     Pos .= pos_out
+    return out
+end
+
+"""
+    sphmap_projected(pos_in, HSML, M, Rho, Bin_Q, Weights; projection, param, kernel, ...)
+
+`map_it`'s projection pre-step (cic_interpolation.jl:331-345) fused into the deposit: `projection` is "xy", "xz",
+"yz" (axis permutation, exact) or a vector of three Euler angles in degrees (rotate_3D).  `pos_in` is only read —
+no `copy(pos_in)`, no rotated array.  `param` is the UNROTATED map; the rotated parameters are built here with the
+reference's own rotate_to_xz_plane(par) / rotate_to_yz_plane(par).
+"""
+function sphmap_projected(pos_in::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; projection="xy", param, kernel,
+                          dimensions::Int=2, calc_mean::Bool=true, reduce_image::Bool=true,
+                          ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
+    perm = C_NULL; rot = C_NULL; par = param
+    if projection == "xz"
+        perm = Int32[0, 2, 1]; par = rotate_to_xz_plane(param)
+    elseif projection == "yz"
+        perm = Int32[1, 2, 0]; par = rotate_to_yz_plane(param)
+    elseif projection isa AbstractVector
+        R = RotXYZ(deg2rad.(projection)...)
+        rot = Float64[R[1, 1], R[1, 2], R[1, 3], R[2, 1], R[2, 2], R[2, 3], R[3, 1], R[3, 2], R[3, 3]]  # row-major
+    elseif projection != "xy"
+        error("projection must be either along in 'xy', 'xz', or 'yz' plane of defined by a vector of Euler angles!")
+    end
+    _, par_centred = center_particles(Matrix{T}(undef, 3, 0), par)   # only the recentred parameters are needed
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+    N = length(m)
+    n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
+    n = par_centred.Npixels[1]
+    out = dimensions == 2 ? Array{Float64,3}(undef, n, n, n_images) : Array{Float64,3}(undef, n, n, n)
+    shift = Float64.(par.center); half = Float64.(par_centred.halfsize)
+    GC.@preserve pos_in hsml m rho bq w out shift half perm rot begin
+        check(ccall((:s2g_sphmap_projected, LIB), Cint,
+                    (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Float64},
+                     Float64, Int64, Int32, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, dimensions, pos_in, hsml, m, rho, bq, w, N, n_images,
+                    T == Float32 ? S2G_F32 : S2G_F64, perm, rot, shift, par.periodic, Float64(par.boxsize), half,
+                    Float64(par_centred.len2pix), n, kernel_id(kernel), calc_mean, reduce_image, false, C_NULL, out,
+                    C_NULL))
+    end
     return out
 end
 

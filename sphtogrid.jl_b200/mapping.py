@@ -74,10 +74,12 @@ def cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=None, *, param: mapping
                    kernel: AbstractSPHKernel, show_progress=False, calc_mean=True, stokes=False, ctx=None,
                    return_stats=False):
     """Underlying function to map SPH data to a 2D grid (cic_2D.jl:103-244).  Returns the flat image
-    (Nx*Ny, N_images+1), weight plane last."""
-    if RM is not None or stokes:
-        raise NotImplementedError("Faraday rotation / Stokes compositing (RM, stokes) is not implemented "
-                                  "(S2G_EUNSUPPORTED): it is order-dependent per pixel (SURVEY.md §8 f4)")
+    (Nx*Ny, N_images+1), weight plane last.
+
+    With `RM` (one Float64 rotation measure per particle) and `stokes=True` the particles are composited in the order
+    given and the Stokes Q/U planes (images 1 and 2) of every pixel that already holds emission are Faraday-rotated
+    by `mod(RM[p]*pix_weight, pi)` first (cic_2D.jl:201-217, cic_shared.jl:129-159).  `RM` without `stokes` is inert
+    in the reference (faraday_rotate_pixel! then only computes the angle), and so it is here."""
     ctx = ctx or default_context()
     pos = _as_pos(Pos)
     n = pos.shape[0]
@@ -86,6 +88,19 @@ def cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=None, *, param: mapping
     npix = int(param.Npixels[0])
     image = np.zeros((npix * npix, nim + 1), order="F")
     st = _lib.Stats()
+    if RM is not None:
+        rm = np.asarray(RM)
+        if rm.dtype != np.float64:  # faraday_rotate_pixel!(…, pRM::Float64, …) has no other method
+            raise TypeError("MethodError: no method matching faraday_rotate_pixel!(::Matrix{Float64}, ::Int64, "
+                            f"::{rm.dtype}, ::Float64, ::Bool): RM must be Float64")
+        rm = np.ascontiguousarray(rm)
+        if rm.shape[0] < n:
+            raise IndexError(f"BoundsError: attempt to access {rm.shape[0]}-element Vector{{Float64}} at index [{n}]")
+        check(lib().s2g_deposit_2d_rm(ctx.handle, ptr(_prep(pos, dt)), ptr(_prep(HSML, dt)), ptr(_prep(M, dt)),
+                                      ptr(_prep(Rho, dt)), ptr(bq), ptr(_prep(Weights, dt)), ptr(rm), n, nim, code,
+                                      float(param.len2pix), npix, int(param.Npixels[1]), _kernel_id(kernel),
+                                      int(calc_mean), int(bool(stokes)), ptr(image), C.byref(st)))
+        return (image, st.asdict()) if return_stats else image
     check(lib().s2g_deposit_2d(ctx.handle, ptr(_prep(pos, dt)), ptr(_prep(HSML, dt)), ptr(_prep(M, dt)),
                                ptr(_prep(Rho, dt)), ptr(bq), ptr(_prep(Weights, dt)), n, nim, code,
                                float(param.len2pix), npix, int(param.Npixels[1]), _kernel_id(kernel), int(calc_mean),
@@ -199,14 +214,19 @@ def part_weight_spectroscopic(rho, T_K):
 def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: mappingParameters,
                kernel: AbstractSPHKernel, show_progress: bool = True, parallel: bool = False,
                reduce_image: bool = True, return_both_maps: bool = False, dimensions: int = 2,
-               calc_mean: bool = False, stokes: bool = False, sort_z: bool = False, ctx=None, return_stats=False):
+               calc_mean: bool = False, stokes: bool = False, sort_z: bool = False, ctx=None, return_stats=False,
+               _projection=None):
     """Maps the data in `Bin_Quant` to a grid (cic_interpolation.jl:35-273).
 
     `Pos` is recentred IN PLACE like the reference does.  `parallel=True` shards the particles over the ranks of an
     initialised torch.distributed process group (one GPU per rank) with `domain_decomposition` and sums the partial
     flat images with an NCCL all-reduce before the division (`image = sum(fetch.(futures))`, :199/:256)."""
-    if stokes or RM is not None:
-        raise NotImplementedError("stokes / RM mapping is not implemented (S2G_EUNSUPPORTED, SURVEY.md §8 f4)")
+    if stokes:
+        # cic_interpolation.jl:74-81: back-to-front order, serial.  NB the reference does NOT forward `stokes` to
+        # cic_mapping_2D (:152-155), so through sphMapping the RM never rotates anything; reproduced: the map is
+        # the z-sorted deposit.  Call cic_mapping_2D(..., RM, stokes=True) directly for the Faraday compositing.
+        sort_z = True
+        parallel = False
     if dimensions not in (2, 3):
         return None  # the reference falls through both branches and returns nothing
     ctx = ctx or default_context()
@@ -223,6 +243,20 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
     kid = _kernel_id(kernel)
     hs, mm, rr, ww = _prep(HSML, dt), _prep(M, dt), _prep(Rho, dt), _prep(Weights, dt)
 
+    if _projection is not None and (parallel or sort_z or pos.dtype != dt):
+        # map_it's projection on a path that is not the fused single-call one: rotate the (copied) positions on the
+        # host like the reference does, then continue unprojected
+        from .rotate import _permute, apply_matrix
+        perm, rot = _projection
+        _projection = None
+        if perm is not None:
+            _permute(perm, pos)
+        else:
+            pos = apply_matrix(rot, pos)
+            dt, code = _common_dtype(pos, HSML, M, Rho, Bin_Quant, Weights)
+            bq, nim = _binq(Bin_Quant, n, dt)
+            hs, mm, rr, ww = _prep(HSML, dt), _prep(M, dt), _prep(Rho, dt), _prep(Weights, dt)
+
     if parallel:
         from .distributed import sph_mapping_sharded
         return sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid, dimensions, calc_mean,
@@ -235,7 +269,8 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
         x = np.ascontiguousarray(pos[sel])
         bqs = np.ascontiguousarray(bq[sel])
         if dimensions == 2:
-            image = cic_mapping_2D(x, hs[sel], mm[sel], rr[sel], bqs, ww[sel], param=par, kernel=kernel,
+            rms = None if RM is None else np.ascontiguousarray(np.asarray(RM)[sel])
+            image = cic_mapping_2D(x, hs[sel], mm[sel], rr[sel], bqs, ww[sel], rms, param=par, kernel=kernel,
                                    calc_mean=calc_mean, ctx=ctx)
             if return_both_maps:
                 return image
@@ -249,7 +284,18 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
     else:
         out = np.zeros((npix, npix, npix), order="F")
     st = _lib.Stats()
-    if pos.dtype == dt:
+    if _projection is not None:
+        # map_it(projection=...): permutation / rotation applied inside the position load of the same fused call;
+        # the positions are a private copy of map_it, nothing is written back
+        perm, rot = _projection
+        cperm = (C.c_int32 * 3)(*perm) if perm is not None else None
+        crot = (C.c_double * 9)(*np.asarray(rot, dtype=np.float64).ravel()) if rot is not None else None
+        check(lib().s2g_sphmap_projected(ctx.handle, dimensions, ptr(pos), ptr(hs), ptr(mm), ptr(rr), ptr(bq), ptr(ww),
+                                         n, nim, code, cperm, crot, dbl3(param.center), int(param.periodic),
+                                         float(param.boxsize), dbl3(par.halfsize), float(par.len2pix), npix, kid,
+                                         int(calc_mean), int(bool(reduce_image)), int(both), None, ptr(out),
+                                         C.byref(st)))
+    elif pos.dtype == dt:
         # fused: centre (in the precision of Pos) + filter + deposit + reduce on the device; the recentred
         # positions come back so that the caller's Pos is mutated like in the reference (Q1)
         pos_out = np.empty_like(pos)
@@ -277,12 +323,14 @@ def map_it(pos_in, hsml, mass, rho, bin_q, weights, RM=None, *, param: mappingPa
     from .kernels import WendlandC6
     kernel = kernel or WendlandC6(2)
     pos = np.array(_as_pos(pos_in), copy=True)   # pos = copy(pos_in): the caller's positions stay untouched
-    if projection != "xy":
-        raise NotImplementedError("projection rotation is a pre-step outside the deposit path (SURVEY.md §8 f3)")
+    from .rotate import projection_of
+    perm, rot, par, projection = projection_of(projection, param)   # cic_interpolation.jl:331-345
+    proj = None if (perm is None and rot is None) else (perm, rot)
     import torch.distributed as dist
     par_ok = bool(parallel) and dist.is_available() and dist.is_initialized()
-    m = sphMapping(pos, hsml, mass, rho, bin_q, weights, RM, param=param, kernel=kernel, show_progress=show_progress,
-                   parallel=par_ok, reduce_image=reduce_image, calc_mean=calc_mean, sort_z=sort_z, stokes=stokes)
+    m = sphMapping(pos, hsml, mass, rho, bin_q, weights, RM, param=par, kernel=kernel, show_progress=show_progress,
+                   parallel=par_ok, reduce_image=reduce_image, calc_mean=calc_mean, sort_z=sort_z, stokes=stokes,
+                   _projection=proj)
     if renorm:
         m /= np.max(m)
     if write_fits and (not par_ok or dist.get_rank() == 0):
