@@ -16,7 +16,8 @@ from .rotate import (rotate_3D, rotate_3D_, rotate_to_xz_plane, rotate_to_yz_pla
                      project_along_axis, euler_matrix)
 from . import distributed, io  # noqa: F401
 from .distributed import distributed_cic_map, distributed_allsky_map  # noqa: F401
-from .io import write_fits_image, read_fits_image  # noqa: F401
+from .io import (write_fits_image, read_fits_image, read_allsky_fits_image, save_healpix_fits,  # noqa: F401
+                 read_healpix_fits, write_vtk_image, get_map_grid_3D)
 
 __all__ = ["sphMapping", "map_it", "mappingParameters", "healpix_map", "Cubic", "Quintic", "WendlandC2", "WendlandC4",
            "WendlandC6", "WendlandC8", "cic_deposit", "tsc_deposit", "Context"]

@@ -152,7 +152,8 @@ def distributed_cic_map(cic_filename, Nsubfiles, mapping_function, param, Nimage
         raise ValueError("Only 2D and 3D are possible")
     if write and world()[1] == 0:
         if Ndim == 3 and vtk:
-            np.save(cic_filename + ".npy", image)  # VTK output is outside this path
+            from .io import write_vtk_image
+            write_vtk_image(cic_filename, image, "map", param, snap=snap, units=units)  # cic.jl:96-98
         else:
             from .io import write_fits_image
             write_fits_image(cic_filename, image, param, snap=snap, units=units)
@@ -174,5 +175,6 @@ def distributed_allsky_map(allsky_filename, Nside, Nsubfiles, mapping_function, 
         ok = np.isfinite(sum_w) & (sum_w != 0)
         sum_a[ok] /= sum_w[ok]
     if write and world()[1] == 0:
-        np.save(allsky_filename + ".npy", sum_a)  # HEALPix FITS tables are outside this path
+        from .io import save_healpix_fits
+        save_healpix_fits(allsky_filename, sum_a)  # saveToFITS(sum_allsky, allsky_filename), healpix.jl:73-77
     return sum_a, sum_w

@@ -49,3 +49,64 @@ def test_reference_fits_fixtures_if_present(s2g):
     img, par, snap, units = s2gio.read_fits_image(path)
     assert hashlib.sha256(np.asfortranarray(img).astype(">f8").tobytes(order="F")).hexdigest() == st["sha256_be_f64"]
     assert par.Npixels[0] == 256 and par.pixelSideLength == 0.02109375 and units == "g/cm^2"
+
+
+# ---- allsky image (io.jl:62-89, :146-186), HEALPix table (saveToFITS, distributed_mapping/healpix.jl:73-77), VTK
+def test_allsky_fits_image_round_trip(tmp_path):
+    import __graft_entry__ as ge
+    s2g = ge.load_package()
+    rng = np.random.default_rng(0)
+    img = rng.normal(size=(12 * 8 * 8,))
+    fn = str(tmp_path / "allsky.fits")
+    s2g.write_fits_image(fn, img, units="erg/s", snap=42)
+    back, snap, units = s2g.read_allsky_fits_image(fn)
+    assert np.array_equal(back, img) and snap == 42 and units == "erg/s"
+    assert os.path.getsize(fn) % 2880 == 0
+
+
+def test_healpix_fits_table_round_trip(tmp_path):
+    import __graft_entry__ as ge
+    s2g = ge.load_package()
+    nside = 16
+    px = np.random.default_rng(1).normal(size=12 * nside * nside)
+    fn = str(tmp_path / "map.fits")
+    open(fn, "wb").write(b"stale")          # the reference removes an existing file first
+    s2g.save_healpix_fits(fn, px)
+    back, hdr = s2g.read_healpix_fits(fn)
+    assert np.array_equal(back, px)
+    assert hdr["PIXTYPE"] == "HEALPIX" and hdr["ORDERING"] == "RING" and hdr["NSIDE"] == nside
+    assert hdr["TTYPE1"] == "PIXVALS" and hdr["TFORM1"] == "1D" and hdr["NAXIS2"] == px.size
+    assert hdr["FIRSTPIX"] == 0 and hdr["LASTPIX"] == px.size - 1 and hdr["INDXSCHM"] == "IMPLICIT"
+    assert os.path.getsize(fn) % 2880 == 0
+    with pytest.raises(ValueError):
+        s2g.save_healpix_fits(fn, np.zeros(100))
+
+
+def test_vtk_rectilinear_grid(tmp_path):
+    import re
+    import struct
+    import __graft_entry__ as ge
+    s2g = ge.load_package()
+    par = s2g.mappingParameters(center=[1.0, 2.0, 3.0], x_size=4.0, y_size=4.0, z_size=4.0, Npixels=6)
+    x, y, z = s2g.get_map_grid_3D(par)
+    assert x[0] == par.x_lim[0] + 0.5 * par.pixelSideLength and y[-1] == par.y_lim[0] + 5.5 * par.pixelSideLength
+    assert np.array_equal(z, y)             # reconstruct_grid.jl:41-43 starts z from y_lim — reproduced
+    img = np.random.default_rng(2).normal(size=(6, 6, 6))
+    fn = s2g.write_vtk_image(str(tmp_path / "cube"), img, "map", par, units="g/cm^3", snap=7)
+    assert fn.endswith(".vtr")
+    raw = open(fn, "rb").read()
+    head, tail = raw.split(b'<AppendedData encoding="raw">\n_', 1)
+    assert b'type="RectilinearGrid"' in head and b'WholeExtent="0 5 0 5 0 5"' in head and b'Name="map"' in head
+    offs = {m.group(1).decode(): int(m.group(2)) for m in re.finditer(rb'Name="(\w+)"[^>]*offset="(\d+)"', head)}
+    n, = struct.unpack_from("<Q", tail, offs["map"])
+    assert n == img.size * 8
+    back = np.frombuffer(tail, dtype="<f8", count=img.size, offset=offs["map"] + 8).reshape(img.shape, order="F")
+    assert np.array_equal(back, img)
+    nx, = struct.unpack_from("<Q", tail, offs["x"])
+    assert np.array_equal(np.frombuffer(tail, dtype="<f8", count=nx // 8, offset=offs["x"] + 8), x)
+    ns, = struct.unpack_from("<Q", tail, offs["Snap"])
+    assert ns == 8 and struct.unpack_from("<q", tail, offs["Snap"] + 8)[0] == 7
+    nu, = struct.unpack_from("<Q", tail, offs["Units"])
+    assert tail[offs["Units"] + 8: offs["Units"] + 8 + nu] == b"g/cm^3\0"
+    with pytest.raises(ValueError):
+        s2g.write_vtk_image(str(tmp_path / "bad"), img[:5], "map", par)
