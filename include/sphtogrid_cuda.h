@@ -48,7 +48,7 @@ typedef enum {
     S2G_EINVAL = -1,       /* bad argument */
     S2G_ECUDA = -2,        /* CUDA runtime error / no device */
     S2G_ENOMEM = -3,       /* device or host allocation failed */
-    S2G_EUNSUPPORTED = -4, /* stokes / RM / fp32-accumulate: not implemented */
+    S2G_EUNSUPPORTED = -4, /* reserved (an fp32-accumulate mode is not built) */
     S2G_EINTERNAL = -5
 } s2g_status;
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Generates tests/golden/oracle_vectors.npz: seeded inputs and the CPU oracle's outputs for one small case per path
-(2D multi-image, 3D, HEALPix, CIC/TSC).  The vectors pin the oracle against silent drift (CPU test) and give the GPU
+(2D multi-image, 3D, HEALPix, CIC/TSC, Stokes/Faraday compositing).  The vectors pin the oracle against silent drift (CPU test) and give the GPU
 parity tests a committed target that does not depend on the oracle being rebuilt on the GPU box."""
 import os
 import sys
@@ -41,8 +41,18 @@ def main():
     out["hp_wmap"] = wm
     out["cic3d"] = orc.stencil_deposit(2, 3, pos, q, npix3 / 10.0, npix3, False)
     out["tsc2d"] = orc.stencil_deposit(3, 2, pos, q, npix2 / 10.0, npix2, True)
+    # ordered Stokes/Faraday compositing (cic_mapping_2D with RM, stokes=true): particles far -> near, RM*pw = O(1) rad
+    rng = np.random.default_rng(4)
+    order = np.argsort(pos[:, 2], kind="stable")[::-1]
+    QU = rng.normal(size=(pos.shape[0], 2))
+    rm = rng.normal(size=pos.shape[0]) * 0.3
+    out["stokes_order"] = order
+    out["stokes_qu"] = QU
+    out["stokes_rm"] = rm
+    out["stokes_WendlandC4"] = orc.cic_mapping_2d_rm(pos[order], hsml[order], m[order], rho[order], QU[order], w[order],
+                                                     rm[order], npix2 / 10.0, npix2, "WendlandC4", 2, True, True)[0]
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "oracle_vectors.npz"), **out)
-    print({k: (v.shape, float(np.nansum(v))) for k, v in out.items() if k.startswith(("map", "hp_m", "hp_w", "cic", "tsc"))})
+    print({k: (v.shape, float(np.nansum(v))) for k, v in out.items() if k.startswith(("map", "hp_m", "hp_w", "cic", "tsc", "stokes_W"))})
 
 
 if __name__ == "__main__":

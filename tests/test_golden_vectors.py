@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from util import assert_parity
+from test_stokes_rm import polarised_parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = np.load(os.path.join(ROOT, "tests", "golden", "oracle_vectors.npz"))
@@ -25,6 +26,11 @@ def test_oracle_reproduces_golden_vectors(oracle):
     assert np.array_equal(a, G["hp_map"]) and np.array_equal(wm, G["hp_wmap"])
     assert np.array_equal(oracle.stencil_deposit(2, 3, pos, q, 2.0, 20, False), G["cic3d"])
     assert np.array_equal(oracle.stencil_deposit(3, 2, pos, q, 6.4, 64, True), G["tsc2d"])
+    o = G["stokes_order"]
+    st = oracle.cic_mapping_2d_rm(pos[o], hsml[o], m[o], rho[o], G["stokes_qu"][o], w[o], G["stokes_rm"][o], 6.4, 64,
+                                  "WendlandC4", 2, True, True)[0]
+    # atan / sin / cos come from libm: allow an ulp-level drift between libm builds instead of demanding identical bits
+    polarised_parity(st, G["stokes_WendlandC4"], 2, 1e-13, "golden stokes (oracle)")
 
 
 @pytest.mark.gpu
@@ -44,6 +50,11 @@ def test_gpu_matches_golden_vectors(s2g, strategy):
     a, wm = s2g.healpix_deposit(G["hp_pos"], hsml * 12.0, m, rho, q, w, 16, s2g.WendlandC4(2), True, ctx=ctx)
     assert_parity(a, G["hp_map"], rtol=1e-9, what="golden healpix map")
     assert_parity(wm, G["hp_wmap"], rtol=1e-9, what="golden healpix weights")
+    if strategy == "auto":
+        o = G["stokes_order"]
+        st = s2g.cic_mapping_2D(pos[o], hsml[o], m[o], rho[o], G["stokes_qu"][o], w[o], G["stokes_rm"][o], param=p2,
+                                kernel=s2g.WendlandC4(2), calc_mean=True, stokes=True, ctx=ctx)
+        polarised_parity(st, G["stokes_WendlandC4"], 2, 1e-10, "golden stokes")
     assert_parity(s2g.cic_deposit(pos, q, param=p3, dimensions=3, average=False, ctx=ctx), G["cic3d"], rtol=1e-12,
                   what="golden CIC")
     assert_parity(s2g.tsc_deposit(pos, q, param=p2, dimensions=2, average=False, periodic=True, ctx=ctx), G["tsc2d"],
