@@ -14,7 +14,7 @@ from .healpix import healpix_map, healpix_deposit, filter_sort_particles, find_i
 from .stencils import cic_deposit, tsc_deposit  # noqa: F401
 from .rotate import (rotate_3D, rotate_3D_, rotate_to_xz_plane, rotate_to_yz_plane,  # noqa: F401
                      project_along_axis, euler_matrix)
-from . import distributed, io  # noqa: F401
+from . import distributed, gadget, io  # noqa: F401
 from .distributed import distributed_cic_map, distributed_allsky_map  # noqa: F401
 from .io import (write_fits_image, read_fits_image, read_allsky_fits_image, save_healpix_fits,  # noqa: F401
                  read_healpix_fits, write_vtk_image, get_map_grid_3D)

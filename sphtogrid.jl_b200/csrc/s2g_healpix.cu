@@ -552,13 +552,27 @@ __device__ __forceinline__ void hp_process_batch(const HpGeom& g, const Disc& d,
     }
 }
 
-template <int KID>
+// COOP = false: one warp per particle (dynamic queue over all particles, skipping those flagged `heavy`).
+// COOP = true : one CTA (8 warps) per particle of `heavy_list` — the ring batches of both passes are dealt round-robin
+//               to the warps and the pass-A sums are combined through shared memory.  A disc of ~10^6 pixels (a
+//               particle close to the observer) otherwise occupies a single warp for tens of milliseconds and the
+//               whole device waits for it.
+template <int KID, bool COOP>
 __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, int calc_mean,
                                                     const unsigned char* __restrict__ take,
-                                                    const unsigned* __restrict__ order, bool use_bulk,
+                                                    const unsigned* __restrict__ order,
+                                                    const unsigned char* __restrict__ heavy,
+                                                    const unsigned* __restrict__ heavy_list,
+                                                    const unsigned* __restrict__ n_heavy, bool use_bulk,
                                                     double* __restrict__ amap, double* __restrict__ wmap,
                                                     unsigned long long* __restrict__ counters)
 {
+    __shared__ long long s_pick;
+    __shared__ double s_redd[8][2];
+    __shared__ long long s_redl[8][2];
+    constexpr int NW = COOP ? 8 : 1;          // warps per particle
+    constexpr long long BR = COOP ? 4 : 32;   // rings per batch: small batches interleave the short polar and the
+                                              // long equatorial rings of a big disc evenly over the 8 warps
     extern __shared__ __align__(16) unsigned char hp_smem[];
     RingBatch* s_rb = reinterpret_cast<RingBatch*>(hp_smem);
     HpStage* s_st = reinterpret_cast<HpStage*>(hp_smem + 8 * sizeof(RingBatch));
@@ -570,12 +584,23 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
     const double belt_inv_den = 1.0 / __dmul_rn(2.0, (double)g.nside);
     double lane_c, lane_s;
     sincospi((double)lane * belt_inv_den, &lane_s, &lane_c);
+    const int wsub = COOP ? wq : 0;           // this warp's slot among the warps sharing the particle
     for (;;) {
         long long p = 0;
-        if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
-        p = __shfl_sync(0xffffffffu, p, 0);
-        if (p >= P.n) break;
-        if (order) p = order[p];               // processing order: by sky region (L2 locality of the map updates)
+        if (COOP) {
+            __syncthreads();                   // previous particle's shared sums are consumed
+            if (threadIdx.x == 0) s_pick = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
+            __syncthreads();
+            p = s_pick;
+            if (p >= (long long)*n_heavy) break;
+            p = heavy_list[p];
+        } else {
+            if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (p >= P.n) break;
+            if (order) p = order[p];           // processing order: by sky region (L2 locality of the map updates)
+            if (heavy && heavy[p]) continue;   // done by the cooperative launch
+        }
         if (take && !take[p]) continue;        // not selected by filter_sort_particles
         const double q = ld_in(P.binq, p, P.in_dtype);
         if (!calc_mean && q == 0.0) continue;  // main.jl:160-165
@@ -607,13 +632,14 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         long long n_in = 0, n_tot = 0;
         bool found_c = false;
         __syncwarp();
-        for (long long base = 0; base < nrings; base += 32) {
-            const int nb = (int)min(32LL, nrings - base);
+        for (long long base = BR * wsub; base < nrings; base += BR * NW) {
+            const int nb = (int)min(BR, nrings - base);
             hp_process_batch<KID, false>(g, d, f, rb, d.ring_first + base, nb, true, lane, 0.0, false, q, q_finite, amap,
                                          wmap, sw, sa, n_in, n_tot, found_c, stg, piece_no, false);
-            if (base + 32 < nrings) __syncwarp();
+            if (base + BR * NW < nrings) __syncwarp();
         }
         found_c = __any_sync(0xffffffffu, found_c);
+        if (COOP) found_c = __syncthreads_or(found_c ? 1 : 0) != 0;
         // the centre pixel, when the disc walk did not visit it (push! + unique!)
         double cA = 0.0, cwk = 0.0;
         bool c_inside = false;
@@ -640,15 +666,22 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
             sincospi(((double)(d.cpix - sp + 1) - c_rt.off) * c_rt.inv_den, &s_, &c_);
             const double ez = c_rt.ct - f.uz;
             hp_pixel<KID>(f, c_rt.st, ez * ez, c_, s_, cA, cwk, c_inside);
-            if (lane == 0) {
+            if (lane == 0 && wsub == 0) {
                 sa += cA;
                 if (c_inside) { sw = fma(cwk, cA, sw); ++n_in; }
             }
-            ++n_tot;
+            if (wsub == 0) ++n_tot;
         }
         sw = warp_sum(sw);
         sa = warp_sum(sa);
         n_in = warp_sum_ll(n_in);
+        if (COOP) {  // combine the warps' partial sums, every warp in the same order -> identical normalisation
+            if (lane == 0) { s_redd[wq][0] = sw; s_redd[wq][1] = sa; s_redl[wq][0] = n_in; s_redl[wq][1] = n_tot; }
+            __syncthreads();
+            sw = 0.0; sa = 0.0; n_in = 0; n_tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sw += s_redd[k][0]; sa += s_redd[k][1]; n_in += s_redl[k][0]; n_tot += s_redl[k][1]; }
+        }
 
         // ---- normalisation (pixel_weights.jl:119-137, main.jl:32-33, :188-193)
         bool fb = false;
@@ -657,7 +690,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
             fb = true;
             n_distr = (double)n_tot;
             wpp = (sa != 0.0) ? n_distr / sa : 1.0;
-            if (lane == 0) ++fallback;
+            if (lane == 0 && wsub == 0) ++fallback;
         } else {
             n_distr = (double)n_in;
             wpp = n_distr / sw;
@@ -674,13 +707,14 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
             double d0 = 0.0, d1 = 0.0;
             long long l0 = 0, l1 = 0;
             bool b0 = false;
-            for (long long base = 0; base < nrings; base += 32) {
-                const int nb = (int)min(32LL, nrings - base);
+            for (long long base = BR * wsub; base < nrings; base += BR * NW) {
+                const int nb = (int)min(BR, nrings - base);
                 __syncwarp();
-                hp_process_batch<KID, true>(g, d, f, rb, d.ring_first + base, nb, nrings > 32, lane, area_norm, fb, q,
+                hp_process_batch<KID, true>(g, d, f, rb, d.ring_first + base, nb, COOP || nrings > 32, lane, area_norm, fb, q,
                                             q_finite, amap, wmap, d0, d1, l0, l1, b0, stg, piece_no, use_bulk);
             }
         }
+        if (wsub != 0) continue;  // per-particle bookkeeping and the centre pixel: once
         if (lane == 0) touched += (unsigned long long)n_tot;
         if (!found_c && lane == 0) {
             const double pw = area_norm * (fb ? 1.0 : cwk) * cA;
@@ -745,6 +779,18 @@ __global__ void __launch_bounds__(256) k_hp_order_keys(s2g_particles P, HpGeom g
     idx[p] = (unsigned)p;
 }
 
+// flags the particles whose disc spans at least `min_rings` pixel rings (angular radius >= min_rings/2 pixels)
+__global__ void __launch_bounds__(256) k_hp_heavy(s2g_particles P, double min_radius, unsigned char* __restrict__ heavy)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const double x = ld_pos(P, p, 0), y = ld_pos(P, p, 1), z = ld_pos(P, p, 2);
+    const double dx = sqrt(x * x + y * y + z * z);
+    const double hs = ld_in(P.hsml, p, P.in_dtype);
+    // asin(hs/dx) >= min_radius  <=>  hs >= dx*sin(min_radius)  (min_radius < pi/2); dx < hs particles are skipped
+    heavy[p] = (dx >= hs && hs >= dx * sin(min_radius)) ? 1 : 0;
+}
+
 template <int KID>
 int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned char* take,
                      double* amap, double* wmap)
@@ -778,16 +824,50 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
         ctx->launches += 4;
         order = (const unsigned*)d_i2;
     }
-    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const size_t smem = 8 * (sizeof(RingBatch) + sizeof(HpStage));
     static bool attr_set = false;
     if (!attr_set) {
-        S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    // particles with very large discs (close to the observer) first, one CTA each: S2G_HP_COOP_RINGS (default 512
+    // rings = an angular radius of 256 pixels, >= 2*10^5 pixels per particle; 0 switches the split off)
+    long long coop_rings = 512;
+    if (const char* e = getenv("S2G_HP_COOP_RINGS")) coop_rings = atoll(e);
+    const unsigned char* d_heavy = nullptr;
+    if (coop_rings > 0 && 0.5 * (double)coop_rings * g.ang_pix < 1.5) {
+        void *d_h, *d_list, *d_nh, *d_tmp;
+        S2G_TRY(s2g_scratch(ctx, "hp_heavy", (size_t)P.n, &d_h));
+        S2G_TRY(s2g_scratch(ctx, "hp_heavy_list", sizeof(unsigned) * (size_t)P.n, &d_list));
+        S2G_TRY(s2g_scratch(ctx, "hp_heavy_n", sizeof(unsigned), &d_nh));
+        const int php = s2g_phase_begin(ctx, PH_PREP);
+        k_hp_heavy<<<(int)((P.n + 255) / 256), 256, 0, ctx->stream>>>(P, 0.5 * (double)coop_rings * g.ang_pix,
+                                                                     (unsigned char*)d_h);
+        S2G_CUDA(cudaGetLastError());
+        cub::CountingInputIterator<unsigned> ids(0u);
+        size_t tb = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb, ids, (const unsigned char*)d_h, (unsigned*)d_list, (unsigned*)d_nh,
+                                   (int)P.n, ctx->stream);
+        S2G_TRY(s2g_scratch(ctx, "hp_heavy_tmp", tb + 16, &d_tmp));
+        S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)d_h, (unsigned*)d_list,
+                                            (unsigned*)d_nh, (int)P.n, ctx->stream));
+        s2g_phase_end(ctx, php);
+        S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+        const int phc = s2g_phase_begin(ctx, PH_DEPOSIT);
+        k_healpix<KID, true><<<ctx->sm_count * 2, 256, smem, ctx->stream>>>(
+            P, g, calc_mean, take, nullptr, nullptr, (const unsigned*)d_list, (const unsigned*)d_nh, use_bulk, amap,
+            wmap, ctx->d_counters);
+        s2g_phase_end(ctx, phc);
+        S2G_CUDA(cudaGetLastError());
+        ctx->launches += 3;
+        d_heavy = (const unsigned char*)d_h;
+    }
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     int blocks = (int)std::min<long long>((P.n + 7) / 8, (long long)ctx->sm_count * 2);
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_healpix<KID><<<max(blocks, 1), 256, smem, ctx->stream>>>(P, g, calc_mean, take, order, use_bulk, amap, wmap, ctx->d_counters);
+    k_healpix<KID, false><<<max(blocks, 1), 256, smem, ctx->stream>>>(P, g, calc_mean, take, order, d_heavy, nullptr,
+                                                                      nullptr, use_bulk, amap, wmap, ctx->d_counters);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;

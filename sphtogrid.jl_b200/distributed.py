@@ -123,19 +123,32 @@ def _my_jobs(n_subfiles: int):
     return range(rank, n_subfiles, ws)
 
 
+def _results(jobs, mapping_function, loader):
+    """`mapping_function(subfile)` per job; with a `loader`, sub-file k+1 is read on a background thread while the
+    device works on sub-file k and the function is called as `mapping_function(subfile, loader(subfile))`."""
+    if loader is None:
+        for job in jobs:
+            yield mapping_function(job)
+    else:
+        from .gadget import SnapshotPrefetcher
+        for job, data in SnapshotPrefetcher(jobs, loader):
+            yield mapping_function(job, data)
+
+
 def distributed_cic_map(cic_filename, Nsubfiles, mapping_function, param, Nimages=1, *, reduce_image=True, Ndim=2,
-                        snap=0, units="", vtk=True, write=True):
+                        snap=0, units="", vtk=True, write=True, loader=None):
     """Mirror of distributed_cic_map (src/distributed_mapping/cic.jl:24-110): one map per sub-snapshot file
     (`mapping_function(subfile) -> (map(s), weight_map)`, e.g. the two parts of
     `sphMapping(...; return_both_maps=true)`), summed with the reference's NaN/Inf guard, reduced once, saved.
-    Ranks split the files; the partial sums are combined with one all-reduce.  Returns the reduced image."""
+    Ranks split the files; the partial sums are combined with one all-reduce.  Returns the reduced image.
+    `loader(subfile)` (optional, no reference counterpart) separates the file read from the mapping so that the next
+    sub-file is read while the current one is deposited."""
     from .mapping import reduce_image_2D, reduce_image_3D
     n = int(param.Npixels[0])
     n_distr = n ** Ndim
     acc_map = StreamingAccumulator(n_distr * Nimages)
     acc_w = StreamingAccumulator(n_distr)
-    for job in _my_jobs(Nsubfiles):
-        res = mapping_function(job)
+    for res in _results(_my_jobs(Nsubfiles), mapping_function, loader):
         if res is None or res[0] is None:
             continue
         local_map, local_weight = res
@@ -160,14 +173,14 @@ def distributed_cic_map(cic_filename, Nsubfiles, mapping_function, param, Nimage
     return image
 
 
-def distributed_allsky_map(allsky_filename, Nside, Nsubfiles, mapping_function, *, reduce_image=True, write=False):
+def distributed_allsky_map(allsky_filename, Nside, Nsubfiles, mapping_function, *, reduce_image=True, write=False,
+                           loader=None):
     """Mirror of distributed_allsky_map (src/distributed_mapping/healpix.jl:16-87).  `mapping_function(subfile)` returns
     `(allsky_map, weight_map)` of `healpix_map`.  Returns `(sum_allsky, sum_weights)` (the first divided by the second
     where the weight is finite and non-zero when reduce_image)."""
     npix = 12 * int(Nside) ** 2
     acc_a, acc_w = StreamingAccumulator(npix), StreamingAccumulator(npix)
-    for job in _my_jobs(Nsubfiles):
-        a, w = mapping_function(job)
+    for a, w in _results(_my_jobs(Nsubfiles), mapping_function, loader):
         acc_a.add(a)
         acc_w.add(w)
     sum_a, sum_w = acc_a.result_over_ranks(), acc_w.result_over_ranks()

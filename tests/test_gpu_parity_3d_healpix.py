@@ -250,3 +250,33 @@ def test_deposit_3d_strategies(s2g, oracle, strategy, kernel):
         for k in ("n_mapped", "footprint_pixels", "n_fallback"):
             assert st[k] == ost[k], k
     ctx.close()
+
+
+@pytest.mark.parametrize("coop_rings", ["0", "8", "64"])
+def test_healpix_cooperative_heavy_particles(s2g, oracle, coop_rings, monkeypatch):
+    """Particles whose disc spans many rings are deposited by a whole CTA (ring batches dealt to its 8 warps, pass-A
+    sums combined in shared memory); S2G_HP_COOP_RINGS sets the split (0 = off, default 512).  Same maps, same
+    counters as the oracle whichever way the particles are split — incl. discs over the poles and the centre-pixel and
+    'no pixel centre covered' branches."""
+    monkeypatch.setenv("S2G_HP_COOP_RINGS", coop_rings)
+    nside = 64
+    rng = np.random.default_rng(31)
+    n = 600
+    ang = math.sqrt(4 * math.pi / (12 * nside * nside))
+    pos = rng.normal(size=(n, 3)) * 50.0
+    pos[:6] = [[0, 0, 40.0], [0, 0, -40.0], [1e-7, 0, 30.0], [30.0, 1e-9, 0], [-20.0, 0, 20.0], [0, -35.0, 1.0]]
+    dist = np.linalg.norm(pos, axis=1)
+    hsml = dist * np.sin(ang * rng.uniform(3.0, 12.0, n))
+    hsml[:40] = dist[:40] * np.sin(ang * rng.uniform(20.0, 70.0, 40))   # 40..140 rings: "heavy" for 8 and 64
+    hsml[40:60] = dist[40:60] * np.sin(ang * 0.05)                     # sub-pixel
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 1e4; w = rng.random(n) + 0.5
+    q[100:110] = 0.0
+    for calc_mean in (True, False):
+        a, wm, st = s2g.healpix_deposit(pos, hsml, m, rho, q, w, nside, s2g.WendlandC4(2), calc_mean,
+                                        return_stats=True)
+        ra, rw, ost = oracle.healpix_deposit(pos, hsml, m, rho, q, w, nside, "WendlandC4", 2, calc_mean)
+        for k in ("n_mapped", "n_fallback", "touched_pixels"):
+            assert st[k] == ost[k], (k, st[k], ost[k])
+        assert_parity(wm, rw, rtol=5e-8, what=f"coop={coop_rings} weights")
+        assert_parity(a, ra, rtol=5e-8, what=f"coop={coop_rings} map")
+        assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12) and math.isclose(a.sum(), ra.sum(), rel_tol=1e-12)
