@@ -130,6 +130,9 @@ __device__ __forceinline__ double shape_s(double s)
     return shape_t<KID>(fma(-s, rsqrt_fast(s), 1.0));
 }
 
+// s < 1.0 for s > 0 (or NaN -> false), decided on the integer pipe from the high word: 1.0 = 0x3ff00000'00000000
+__device__ __forceinline__ bool below_one(double s) { return __double2hiint(s) < 0x3ff00000; }
+
 // v if flag else +0.0, as a data select (keeps the four per-group dependency chains in one straight-line block;
 // a C++ ?: around the kernel evaluation invites the compiler to branch around it per lane)
 __device__ __forceinline__ double select_or_zero(bool flag, double v)

@@ -47,7 +47,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                 for (int q = 0; q < 4; ++q) {
                     const double a = fma(-(double)(ii + q), hinv, xb);
                     const double s = fma(a, a, bc2);
-                    in[q] = (s < 1.0) && (ii + q < ni);
+                    in[q] = below_one(s) && (ii + q < ni);
                     wk[q] = shape_s<KID>(s);
                 }
 #pragma unroll
@@ -145,7 +145,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                 for (int q = 0; q < 4; ++q) {
                     const double a = fma(-(double)(ii + q), hinv, xb);
                     const double s = fma(a, a, bc2);
-                    in[q] = (s < 1.0) && (ii + q < ni);
+                    in[q] = below_one(s) && (ii + q < ni);
                     wk[q] = shape_s<KID>(s);
                 }
 #pragma unroll

@@ -153,7 +153,7 @@ __device__ __forceinline__ double pass_a_region(double x, double y, double h, do
                     const int i = i0 + k;
                     const double a = fma(-(double)(i - ia), hinv, xb);
                     const double s = fma(a, a, b2s);
-                    in[k] = (s < 1.0) && (i <= hi) && !(jin && i >= 0 && i < npix);
+                    in[k] = below_one(s) && (i <= hi) && !(jin && i >= 0 && i < npix);
                     wk[k] = shape_s<KID>(s);
                 }
                 if (i0 <= iEl || i0 + 3 >= iEh) {  // group touches the first / last row: partial overlaps
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                         for (int k = 0; k < 4; ++k) {
                             const double a = fma(-(double)(r4 + k), hinv2, xb);
                             s[k] = fma(a, a, b2);
-                            in[k] = live && (s[k] < 1.0);
+                            in[k] = live && below_one(s[k]);
                             any_in = any_in || in[k];
                         }
                         if (!__any_sync(0xffffffffu, any_in)) continue;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                             const int i = ibase + 2 * (r4 + k);
                             const double a = fma(-(double)(r4 + k), hinv2, xb);
                             s[k] = fma(a, a, b2);
-                            in[k] = live && (s[k] < 1.0) && (i >= g.iMin) && (i <= g.iMax);
+                            in[k] = live && below_one(s[k]) && (i >= g.iMin) && (i <= g.iMax);
                             any_in = any_in || in[k];
                         }
                         if (!__any_sync(0xffffffffu, any_in)) continue;

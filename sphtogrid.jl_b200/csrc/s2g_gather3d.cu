@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_norm3d(s2g_particles P, s2g_geom G, con
                     for (int q = 0; q < 4; ++q) {
                         const double a = fma(-(double)(ii + q), hinv, xb);
                         const double s = fma(a, a, bc2);
-                        in[q] = (s < 1.0) && (ii + q < ni);
+                        in[q] = below_one(s) && (ii + q < ni);
                         wk[q] = shape_s<KID>(s);
                     }
 #pragma unroll
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256, 3) k_gather3d(const GRec3* __restrict__ r
                         const int i = i0 + r4 + q;
                         const double a = fma(-(double)(r4 + q), hinv, xb);
                         s[q] = fma(a, a, bc2);
-                        in[q] = live && (s[q] < 1.0) && (interior || (i >= g.lo[0] && i <= g.hi[0]));
+                        in[q] = live && below_one(s[q]) && (interior || (i >= g.lo[0] && i <= g.hi[0]));
                         any_in = any_in || in[q];
                     }
                     if (!__any_sync(0xffffffffu, any_in)) continue;
