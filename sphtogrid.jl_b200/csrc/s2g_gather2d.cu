@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 const double dy = (j == g.jMin) ? g.dy_lo : ((j == g.jMax) ? g.dy_hi : 1.0);
                 const double dyan = dy * g.an;
                 // pix_weight != 0 test of cic_2D.jl:211 hoisted: wk > 0 inside the disc, so only dy*area_norm decides
-                const bool live = (j >= g.jMin) && (j <= g.jMax) && (b2 < 1.0) && nonzero_bits(dyan);
+                const bool live = (j >= g.jMin) && (j <= g.jMax) && below_one(b2) && nonzero_bits(dyan);
                 if (!__any_sync(0xffffffffu, live)) continue;
                 const double dyanq = dyan * s_q[e];
                 const double xb = center_dist(g.x, id0) * hinv;  // a of this thread's first row

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256, 3) k_gather3d(const GRec3* __restrict__ r
                 const double dy = (j == g.lo[1]) ? g.dlo[1] : ((j == g.hi[1]) ? g.dhi[1] : 1.0);
                 const double dz = (k == g.lo[2]) ? g.dlo[2] : ((k == g.hi[2]) ? g.dhi[2] : 1.0);
                 const double wv = dy * dz * g.vn;
-                const bool live = (j >= g.lo[1]) && (j <= g.hi[1]) && (k >= g.lo[2]) && (k <= g.hi[2]) && (bc2 < 1.0) &&
+                const bool live = (j >= g.lo[1]) && (j <= g.hi[1]) && (k >= g.lo[2]) && (k <= g.hi[2]) && below_one(bc2) &&
                                   nonzero_bits(wv);
                 if (!__any_sync(0xffffffffu, live)) continue;
                 const double wq = dy * dz * g.vq;
