@@ -25,10 +25,13 @@
  *  - HEALPix maps are RING ordered, element p (0-based) = Julia pixels[p+1].
  *  - every function returns S2G_OK (0) or a negative s2g_status; the message is
  *    available from s2g_last_error() (thread-local).  Nothing throws.
- *  - a context is bound to ONE device and is not re-entrant.  Multi-GPU runs use
- *    one process (and one context) per GPU; partial images are combined by the
- *    host layer with NCCL (see sphtogrid.jl_b200/distributed.py), replacing
- *    `sum(fetch.(futures))` of src/cic_interpolation/cic_interpolation.jl:199,256.
+ *  - a context is bound to ONE device and is not re-entrant.  Multi-GPU runs either
+ *    use one process (and one context) per GPU, the partial images being combined
+ *    by the host layer with NCCL (sphtogrid.jl_b200/distributed.py), or ONE process
+ *    with a device group (s2g_group_*, below): the library shards the particles,
+ *    runs one host thread per device and sums the partial images over peer memory
+ *    (NVLink).  Both replace `@spawnat` + `sum(fetch.(futures))` of
+ *    src/cic_interpolation/cic_interpolation.jl:185-199, 244-256.
  *  - there is NO CPU fallback: without a usable CUDA device every compute entry
  *    point fails with S2G_ECUDA.
  */
@@ -258,6 +261,40 @@ S2G_API int s2g_stencil_deposit_dev(s2g_ctx* ctx, int32_t order, int32_t dims, c
 
 /* ---- finite-guarded accumulation of partial maps (src/distributed_mapping/cic.jl:62-70, healpix.jl:44-52) */
 S2G_API int s2g_accumulate_finite_dev(s2g_ctx* ctx, double* sum_dev, const double* local_dev, int64_t n);
+
+/* ---- device group: `parallel=true` of sphMapping (src/cic_interpolation/cic_interpolation.jl:171-215, 236-271) for a
+ *      caller that is ONE process with several visible GPUs (a Julia session without Distributed workers).
+ *      s2g_domain_decomposition  = domain_decomposition (src/parallel/domain_decomp.jl:7-17), 0-based starts; needs no
+ *                                  device.  Slice r of it is what device r of a group deposits.
+ *      s2g_group_init            one context per listed device (a device may be listed more than once); enables peer
+ *                                access between all pairs.  s2g_group_peer_access() == 1: the partial images are summed
+ *                                by direct peer loads; 0 (no P2P, or S2G_GROUP_NO_P2P=1): through peer copies.
+ *      s2g_group_context         the context of rank r, e.g. for s2g_set_strategy / s2g_set_exact_norm.
+ *      s2g_group_sphmap          = s2g_sphmap on the whole arrays: every device centres, filters and deposits its slice
+ *                                into a private flat image (`@spawnat batch[i] cic_mapping_2D(...)`, :185-196), then
+ *                                device r sums pixel slice r of ALL images in rank order (`sum(fetch.(futures))`, :199)
+ *                                fused with the reduce_image epilogue (:212, :234) and writes its slice of `out`.
+ *      s2g_group_healpix_map     = s2g_healpix_map on the whole arrays, incl. the `sorted[sel]` selection over ALL
+ *                                particles (filter_particles.jl:33-41) — made once on device 0 when any particle is
+ *                                outside the shell.
+ *      stats_or_null: array of s2g_group_size() entries, one per device (ms_epilogue = peer sum + reduce_image). */
+typedef struct s2g_group s2g_group;
+S2G_API int s2g_domain_decomposition(int64_t n, int32_t n_parts, int64_t* starts_out, int64_t* counts_out);
+S2G_API int s2g_group_init(const int32_t* devices, int32_t n_devices, s2g_group** out);
+S2G_API int s2g_group_shutdown(s2g_group* grp);
+S2G_API int s2g_group_size(const s2g_group* grp);
+S2G_API int s2g_group_peer_access(const s2g_group* grp);
+S2G_API int s2g_group_context(s2g_group* grp, int32_t rank, s2g_ctx** out);
+S2G_API int s2g_group_sphmap(s2g_group* grp, int32_t dims, const void* pos, const void* hsml, const void* m,
+                             const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images,
+                             int32_t in_dtype, const double shift[3], int32_t periodic, double boxsize,
+                             const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
+                             int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
+                             s2g_stats* stats_or_null);
+S2G_API int s2g_group_healpix_map(s2g_group* grp, const void* pos, const void* hsml, const void* m, const void* rho,
+                                  const void* binq, const void* w, int64_t n, const double center[3],
+                                  const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                                  void* pos_recentred_out, double* map_out, double* wmap_out, s2g_stats* stats_or_null);
 
 /* ---- synthetic "Gadget-like" particle stream, generated on the device, counter-based
  *      (Philox4x32-10 keyed by seed, counter = global particle id) so any sharding sees the same particles.

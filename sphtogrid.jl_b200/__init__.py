@@ -3,7 +3,8 @@
 Host mirror (same names as the Julia package) of the ONE hot path this project accelerates; every compute call goes
 through the C ABI of libsphtogrid_cuda.so (include/sphtogrid_cuda.h).  There is no CPU fallback.
 """
-from ._lib import Context, S2GError, build, default_context, lib, LIB_PATH, EXPORTED_SYMBOLS  # noqa: F401
+from ._lib import (Context, DeviceGroup, S2GError, build, default_context, lib, LIB_PATH,  # noqa: F401
+                   EXPORTED_SYMBOLS)
 from .kernels import (AbstractSPHKernel, Cubic, Quintic, WendlandC2, WendlandC4, WendlandC6,  # noqa: F401
                       WendlandC8)
 from .parameters import mappingParameters, recentred_parameters  # noqa: F401
@@ -20,4 +21,4 @@ from .io import (write_fits_image, read_fits_image, read_allsky_fits_image, save
                  read_healpix_fits, write_vtk_image, get_map_grid_3D)
 
 __all__ = ["sphMapping", "map_it", "mappingParameters", "healpix_map", "Cubic", "Quintic", "WendlandC2", "WendlandC4",
-           "WendlandC6", "WendlandC8", "cic_deposit", "tsc_deposit", "Context"]
+           "WendlandC6", "WendlandC8", "cic_deposit", "tsc_deposit", "Context", "DeviceGroup"]

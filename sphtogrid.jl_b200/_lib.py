@@ -104,6 +104,16 @@ _SIGS = {
     "s2g_stencil_deposit": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _vp, C.POINTER(Stats)]),
     "s2g_stencil_deposit_dev": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _i32, _vp]),
     "s2g_accumulate_finite_dev": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "s2g_domain_decomposition": (C.c_int, [_i64, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "s2g_group_init": (C.c_int, [C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
+    "s2g_group_shutdown": (C.c_int, [_vp]),
+    "s2g_group_size": (C.c_int, [_vp]),
+    "s2g_group_peer_access": (C.c_int, [_vp]),
+    "s2g_group_context": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "s2g_group_sphmap": (C.c_int, [_vp, _i32] + [_vp] * 6 + [_i64, _i32, _i32, _dp, _i32, _f64, _dp, _f64, _i64, _i32,
+                                                            _i32, _i32, _i32, _vp, _vp, C.POINTER(Stats)]),
+    "s2g_group_healpix_map": (C.c_int, [_vp] + [_vp] * 6 + [_i64, _dp, _dp, _i64, _i32, _i32, _vp, _vp, _vp,
+                                                              C.POINTER(Stats)]),
     "s2g_synth_particles_dev": (C.c_int, [_vp, C.c_uint64, _i64, _i64, _i64, _f64, _f64, _f64, _i32] + [_vp] * 5),
     "s2g_microbench": (C.c_int, [_vp, _i32, C.c_uint64, _i32, _dp]),
 }
@@ -190,6 +200,77 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class _BorrowedContext(Context):
+    """A context owned by a DeviceGroup (never shut down on its own)."""
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+
+    def close(self):
+        self._h = _vp()
+
+
+class DeviceGroup:
+    """Several GPUs driven by ONE process (s2g_group_*): what `parallel=true` means for a caller without a process
+    group.  `devices=None` takes every visible device.  A device may be listed more than once."""
+
+    def __init__(self, devices=None, strategy: str = "auto", exact_norm: bool = False):
+        if devices is None:
+            devices = list(range(lib().s2g_device_count()))
+        devices = [int(d) for d in devices]
+        self._h = _vp()
+        arr = (C.c_int32 * max(len(devices), 1))(*devices)
+        check(lib().s2g_group_init(arr, len(devices), C.byref(self._h)))
+        self.devices = devices
+        for r in range(len(devices)):
+            c = self.context(r)
+            if strategy != "auto":
+                c.set_strategy(strategy)
+            if exact_norm:
+                c.set_exact_norm(True)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise S2GError(S2G_EINVAL, "device group was shut down")
+        return self._h
+
+    def __len__(self):
+        return len(self.devices)
+
+    @property
+    def peer_access(self) -> bool:
+        return bool(lib().s2g_group_peer_access(self.handle))
+
+    def context(self, rank: int) -> Context:
+        h = _vp()
+        check(lib().s2g_group_context(self.handle, int(rank), C.byref(h)))
+        return _BorrowedContext(h, self.devices[rank])
+
+    def new_stats(self):
+        return (Stats * len(self.devices))()
+
+    def close(self):
+        if self._h:
+            lib().s2g_group_shutdown(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def domain_decomposition_c(n: int, n_parts: int):
+    """s2g_domain_decomposition: (starts, counts) of parallel/domain_decomp.jl:7-17, 0-based; needs no device."""
+    st = (C.c_int64 * n_parts)()
+    ct = (C.c_int64 * n_parts)()
+    check(lib().s2g_domain_decomposition(int(n), int(n_parts), st, ct))
+    return list(st), list(ct)
 
 
 _default_ctx = None

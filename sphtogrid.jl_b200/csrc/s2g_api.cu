@@ -230,6 +230,7 @@ static int stats_begin(s2g_ctx* ctx, long long n_in)
 }
 
 // copies the device counters back (synchronises the stream)
+int s2g_stats_collect(s2g_ctx* ctx);
 static int stats_collect(s2g_ctx* ctx)
 {
     S2G_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_N * sizeof(unsigned long long),
@@ -258,6 +259,9 @@ static int stats_collect(s2g_ctx* ctx)
     ctx->stats.n_launches = ctx->launches;
     return S2G_OK;
 }
+
+int s2g_stats_collect(s2g_ctx* ctx) { return stats_collect(ctx); }
+int s2g_stats_begin(s2g_ctx* ctx, long long n_in) { return stats_begin(ctx, n_in); }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 {
@@ -344,6 +348,12 @@ static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, cons
     P.n = n;
     P.in_dtype = in_dtype;
     return S2G_OK;
+}
+
+int s2g_stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                        const void* binq, const void* w, int64_t n, int n_images, int in_dtype, s2g_particles& P)
+{
+    return stage_particles(ctx, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, P);
 }
 
 static s2g_particles dev_particles(const void* pos, const void* hsml, const void* m, const void* rho, const void* binq,
@@ -710,29 +720,30 @@ extern "C" int s2g_sphmap_projected_dev(s2g_ctx* ctx, int32_t dims, const void* 
                            periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, accumulate, image_dev);
 }
 
-static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
-                       const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images, int32_t in_dtype,
-                       const int32_t* perm, const double* rot, const double shift[3], int32_t periodic, double boxsize,
-                       const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
-                       int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
-                       s2g_stats* stats)
+// First half of the host sphMapping call, shared with the device-group path (s2g_group.cu): argument checks, H2D
+// staging of the six arrays, zero-filled flat image in the context's "image" scratch buffer, deposit with the fused
+// centre + filter (+ projection), optional recentred positions back to the host.  Records ev[0] (start), ev[1]
+// (inputs resident), ev[2] (deposit enqueued); leaves the stream un-synchronised.
+int s2g_sphmap_stage_deposit(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml,
+                             const void* m, const void* rho, const void* binq, const void* w, int64_t n,
+                             int32_t n_images, int32_t in_dtype, const int32_t* perm, const double* rot,
+                             const double shift[3], int32_t periodic, double boxsize, const double halfsize[3],
+                             double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean, void* pos_recentred_out,
+                             double** image_dev_out)
 {
     S2G_CHECK(ctx != nullptr, S2G_EINVAL, "%s: ctx is NULL", fn);
     S2G_CUDA(cudaSetDevice(ctx->device));
     S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", fn);
     S2G_TRY(check_common(fn, pos, hsml, m, rho, binq, w, n, in_dtype, len2pix, npix, kernel));
-    S2G_CHECK(shift && halfsize && out, S2G_EINVAL, "%s: NULL argument", fn);
+    S2G_CHECK(shift && halfsize, S2G_EINVAL, "%s: NULL argument", fn);
     S2G_CHECK(dims == 2 || n_images == 1, S2G_EINVAL, "%s: 3D maps take a single quantity", fn);
     S2G_CHECK(n_images >= 1 && n_images <= 64, S2G_EINVAL, "%s: n_images out of range", fn);
     S2G_CHECK(dims == 2 || npix <= 2048, S2G_EINVAL, "%s: npix > 2048 not supported in 3D", fn);
     S2G_TRY(stats_begin(ctx, n));
     const size_t ncell = dims == 2 ? (size_t)(npix * npix) : (size_t)(npix * npix * npix);
     const int planes = dims == 2 ? n_images + 1 : 2;
-    const int out_planes = dims == 2 ? n_images : 1;
-    void *dimg, *dred = nullptr;
+    void* dimg;
     S2G_TRY(s2g_scratch(ctx, "image", sizeof(double) * ncell * planes, &dimg));
-    const bool both = dims == 2 && return_both_maps;
-    if (!both) S2G_TRY(s2g_scratch(ctx, "reduced", sizeof(double) * ncell * out_planes, &dred));
     S2G_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     s2g_particles P;
     S2G_TRY(stage_particles(ctx, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, P));
@@ -742,6 +753,7 @@ static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* p
     S2G_TRY(set_projection(fn, P, perm, rot));
     S2G_CHECK(!(P.proj == 2 && pos_recentred_out && in_dtype == S2G_F32), S2G_EINVAL,
               "%s: rotated Float32 positions are Float64 in the reference; pos_recentred_out is not available", fn);
+    // the reference does not forward calc_mean to cic_mapping_3D (cic_interpolation.jl:219-221): default false
     s2g_geom G = make_geom(len2pix, npix, dims == 2 ? n_images : 1, dims == 2 ? calc_mean : 0);
     if (dims == 2)
         S2G_TRY(s2g_launch_deposit_2d(ctx, P, G, kernel, (double*)dimg));
@@ -755,10 +767,32 @@ static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* p
         S2G_CUDA(cudaMemcpyAsync(pos_recentred_out, dpo, 3 * (size_t)n * esize(in_dtype), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     }
+    *image_dev_out = (double*)dimg;
+    return S2G_OK;
+}
+
+static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml, const void* m,
+                       const void* rho, const void* binq, const void* w, int64_t n, int32_t n_images, int32_t in_dtype,
+                       const int32_t* perm, const double* rot, const double shift[3], int32_t periodic, double boxsize,
+                       const double halfsize[3], double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean,
+                       int32_t reduce_image, int32_t return_both_maps, void* pos_recentred_out, double* out,
+                       s2g_stats* stats)
+{
+    S2G_CHECK(out != nullptr, S2G_EINVAL, "%s: out is NULL", fn);
+    double* dimg = nullptr;
+    S2G_TRY(s2g_sphmap_stage_deposit(fn, ctx, dims, pos, hsml, m, rho, binq, w, n, n_images, in_dtype, perm, rot, shift,
+                                     periodic, boxsize, halfsize, len2pix, npix, kernel, calc_mean, pos_recentred_out,
+                                     &dimg));
+    const size_t ncell = dims == 2 ? (size_t)(npix * npix) : (size_t)(npix * npix * npix);
+    const int planes = dims == 2 ? n_images + 1 : 2;
+    const int out_planes = dims == 2 ? n_images : 1;
+    const bool both = dims == 2 && return_both_maps;
     if (both) {
         S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
         S2G_CUDA(cudaMemcpyAsync(out, dimg, sizeof(double) * ncell * planes, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
+        void* dred = nullptr;
+        S2G_TRY(s2g_scratch(ctx, "reduced", sizeof(double) * ncell * out_planes, &dred));
         if (dims == 2)
             S2G_TRY(s2g_launch_reduce_2d(ctx, (const double*)dimg, npix, npix, n_images, reduce_image, (double*)dred));
         else
@@ -887,16 +921,20 @@ extern "C" int s2g_healpix_map_dev(s2g_ctx* ctx, const void* pos, const void* hs
     return S2G_OK;
 }
 
-extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
-                               const void* binq, const void* w, int64_t n, const double center[3],
-                               const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
-                               void* pos_recentred_out, double* map_out, double* wmap_out, s2g_stats* stats)
+// First half of the host healpix_map call, shared with the device-group path: staging, zero-filled maps in the
+// "image" scratch buffer (map at [0, npix), weight map at [npix, 2 npix)), recentre + shell filter + far-to-near
+// selection + particle loop, optional recentred positions back.  Records ev[0..2] like s2g_sphmap_stage_deposit.
+int s2g_healpix_stage_deposit(const char* fn, s2g_ctx* ctx, const void* pos, const void* hsml, const void* m,
+                              const void* rho, const void* binq, const void* w, int64_t n, const double center[3],
+                              const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                              void* pos_recentred_out, double** maps_dev_out, long long* n_selected)
 {
-    CTX_ENTER(ctx);
-    S2G_TRY(check_common(__func__, pos, hsml, m, rho, binq, w, n, S2G_F64, 1.0, 1, kernel));
+    S2G_CHECK(ctx != nullptr, S2G_EINVAL, "%s: ctx is NULL", fn);
+    S2G_CUDA(cudaSetDevice(ctx->device));
+    S2G_TRY(check_common(fn, pos, hsml, m, rho, binq, w, n, S2G_F64, 1.0, 1, kernel));
     S2G_CHECK(nside >= 1 && nside <= 8192 && (nside & (nside - 1)) == 0, S2G_EINVAL,
-              "%s: nside must be a power of two in [1, 8192]", __func__);
-    S2G_CHECK(map_out && wmap_out && center && radius_limits, S2G_EINVAL, "%s: NULL argument", __func__);
+              "%s: nside must be a power of two in [1, 8192]", fn);
+    S2G_CHECK(center && radius_limits, S2G_EINVAL, "%s: NULL argument", fn);
     S2G_TRY(stats_begin(ctx, n));
     const size_t npix = (size_t)(12 * nside * nside);
     void* dmaps;
@@ -908,7 +946,7 @@ extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, 
     S2G_TRY(stage_particles(ctx, pos, hsml, m, rho, binq, w, n, 1, S2G_F64, P));
     S2G_CUDA(cudaMemsetAsync(dmaps, 0, sizeof(double) * npix * 2, ctx->stream));
     S2G_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    P.fuse_center = 1;
+    P.fuse_center = 1;  // Pos .-= center (Float64), no periodic wrap, no box filter
     P.periodic = 0;
     for (int d = 0; d < 3; ++d) { P.shift[d] = center[d]; P.halfsize[d] = 0.0; }
     long long nsel = 0;
@@ -922,8 +960,24 @@ extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, 
         S2G_CUDA(cudaMemcpyAsync(pos_recentred_out, dpo, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     }
+    *maps_dev_out = dmap;
+    if (n_selected) *n_selected = nsel;
+    return S2G_OK;
+}
+
+extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                               const void* binq, const void* w, int64_t n, const double center[3],
+                               const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                               void* pos_recentred_out, double* map_out, double* wmap_out, s2g_stats* stats)
+{
+    S2G_CHECK(map_out && wmap_out, S2G_EINVAL, "%s: NULL argument", __func__);
+    double* dmap = nullptr;
+    long long nsel = 0;
+    S2G_TRY(s2g_healpix_stage_deposit(__func__, ctx, pos, hsml, m, rho, binq, w, n, center, radius_limits, nside,
+                                      kernel, calc_mean, pos_recentred_out, &dmap, &nsel));
+    const size_t npix = (size_t)(12 * nside * nside);
     S2G_CUDA(cudaMemcpyAsync(map_out, dmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
-    S2G_CUDA(cudaMemcpyAsync(wmap_out, dwmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    S2G_CUDA(cudaMemcpyAsync(wmap_out, dmap + npix, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);

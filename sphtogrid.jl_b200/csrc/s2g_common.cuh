@@ -263,6 +263,10 @@ int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, in
                        const unsigned char* take, double* map_dev, double* wmap_dev);
 int s2g_launch_healpix_filtered(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, long long nside,
                                 int kernel, int calc_mean, double* map_dev, double* wmap_dev, long long* n_selected);
+int s2g_hp_radii(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, unsigned long long* keys_dev,
+                 unsigned char* sel_dev, long long* n_selected);
+int s2g_hp_take_mask(s2g_ctx* ctx, const unsigned long long* keys_dev, const unsigned char* sel_dev, long long n,
+                     unsigned char* take_dev);
 int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, long long nside, long long* out_dev,
                               long long cap, long long* count_dev);
 int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const void* q, long long n, int in_dtype,
@@ -271,3 +275,21 @@ int s2g_launch_accumulate_finite(s2g_ctx* ctx, double* sum_dev, const double* lo
 int s2g_launch_synth(s2g_ctx* ctx, uint64_t seed, long long first_id, long long n, long long n_total, double box,
                      double n_ngb, double sigma, int out_dtype, void* pos, void* hsml, void* m, void* rho, void* temp);
 int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double* rate_out);
+
+// first halves of the host entry points s2g_sphmap / s2g_healpix_map (s2g_api.cu), shared with the device group
+int s2g_sphmap_stage_deposit(const char* fn, s2g_ctx* ctx, int32_t dims, const void* pos, const void* hsml,
+                             const void* m, const void* rho, const void* binq, const void* w, int64_t n,
+                             int32_t n_images, int32_t in_dtype, const int32_t* perm, const double* rot,
+                             const double shift[3], int32_t periodic, double boxsize, const double halfsize[3],
+                             double len2pix, int64_t npix, int32_t kernel, int32_t calc_mean, void* pos_recentred_out,
+                             double** image_dev_out);
+int s2g_healpix_stage_deposit(const char* fn, s2g_ctx* ctx, const void* pos, const void* hsml, const void* m,
+                              const void* rho, const void* binq, const void* w, int64_t n, const double center[3],
+                              const double radius_limits[2], int64_t nside, int32_t kernel, int32_t calc_mean,
+                              void* pos_recentred_out, double** maps_dev_out, long long* n_selected);
+// copies the device counters and phase timers into ctx->stats (synchronises the context stream)
+int s2g_stats_collect(s2g_ctx* ctx);
+int s2g_stats_begin(s2g_ctx* ctx, long long n_in);
+// H2D staging of the six particle arrays into the context's scratch buffers
+int s2g_stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
+                        const void* binq, const void* w, int64_t n, int n_images, int in_dtype, s2g_particles& P);

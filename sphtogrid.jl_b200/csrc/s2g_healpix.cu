@@ -825,11 +825,11 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
         order = (const unsigned*)d_i2;
     }
     const size_t smem = 8 * (sizeof(RingBatch) + sizeof(HpStage));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // function attributes are per device; a process may drive several (s2g_group.cu)
+    if (!attr_set[ctx->device & 63]) {
         S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     // particles with very large discs (close to the observer) first, one CTA each: S2G_HP_COOP_RINGS (default 512
     // rings = an angular radius of 256 pixels, >= 2*10^5 pixels per particle; 0 switches the split off)
@@ -901,7 +901,7 @@ int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, in
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256) k_hp_radii(s2g_particles P, double r0, double r1,
-                                                  unsigned long long* __restrict__ keys, unsigned* __restrict__ idx,
+                                                  unsigned long long* __restrict__ keys,
                                                   unsigned char* __restrict__ sel, unsigned long long* nsel)
 {
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -912,11 +912,16 @@ __global__ void __launch_bounds__(256) k_hp_radii(s2g_particles P, double r0, do
         const double dx = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
         s = (r0 <= dx) && (dx <= r1);
         keys[p] = (unsigned long long)__double_as_longlong(dx);  // dx >= 0: the bit pattern orders like the value
-        idx[p] = (unsigned)p;
         sel[p] = s ? 1 : 0;
     }
     const unsigned b = __ballot_sync(0xffffffffu, s);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(nsel, (unsigned long long)__popc(b));
+}
+
+__global__ void __launch_bounds__(256) k_hp_iota(unsigned* __restrict__ idx, long long n)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (unsigned)i;
 }
 
 __global__ void __launch_bounds__(256) k_hp_take(const unsigned* __restrict__ asc, const unsigned char* __restrict__ sel,
@@ -928,46 +933,73 @@ __global__ void __launch_bounds__(256) k_hp_take(const unsigned* __restrict__ as
 }
 }  // namespace
 
-int s2g_launch_healpix_filtered(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, long long nside,
-                                int kernel, int calc_mean, double* amap, double* wmap, long long* n_selected)
+// radii (as sortable keys) and shell mask of the particles of P; *n_selected = particles inside the shell.
+// Synchronises the stream.
+int s2g_hp_radii(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, unsigned long long* keys_dev,
+                 unsigned char* sel_dev, long long* n_selected)
 {
-    if (P.n <= 0) { if (n_selected) *n_selected = 0; return S2G_OK; }
-    const long long n = P.n;
-    void *d_keys, *d_keys2, *d_idx, *d_idx2, *d_sel, *d_take, *d_tmp;
-    S2G_TRY(s2g_scratch(ctx, "hp_keys", sizeof(unsigned long long) * n, &d_keys));
-    S2G_TRY(s2g_scratch(ctx, "hp_idx", sizeof(unsigned) * n, &d_idx));
-    S2G_TRY(s2g_scratch(ctx, "hp_sel", (size_t)n, &d_sel));
+    *n_selected = 0;
+    if (P.n <= 0) return S2G_OK;
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_PAIRS, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = (int)((n + 255) / 256);
-    int ph = s2g_phase_begin(ctx, PH_PREP);
-    k_hp_radii<<<blocks, 256, 0, ctx->stream>>>(P, r0, r1, (unsigned long long*)d_keys, (unsigned*)d_idx,
-                                                (unsigned char*)d_sel, ctx->d_counters + CNT_PAIRS);
+    const int blocks = (int)((P.n + 255) / 256);
+    const int ph = s2g_phase_begin(ctx, PH_PREP);
+    k_hp_radii<<<blocks, 256, 0, ctx->stream>>>(P, r0, r1, keys_dev, sel_dev, ctx->d_counters + CNT_PAIRS);
     S2G_CUDA(cudaGetLastError());
     unsigned long long h_nsel = 0;
     S2G_CUDA(cudaMemcpyAsync(&h_nsel, ctx->d_counters + CNT_PAIRS, sizeof(h_nsel), cudaMemcpyDeviceToHost, ctx->stream));
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->launches += 1;
-    if (n_selected) *n_selected = (long long)h_nsel;
+    *n_selected = (long long)h_nsel;
+    return S2G_OK;
+}
+
+// take[sorted[i]] = 1 for every i with sel[i], sorted = reverse(sortperm(Δx)) (stable ascending radix sort of the
+// radii, read backwards) — the reference's `sorted[sel]` (filter_particles.jl:33-41).  keys/sel/take: n elements on
+// the context's device.
+int s2g_hp_take_mask(s2g_ctx* ctx, const unsigned long long* keys_dev, const unsigned char* sel_dev, long long n,
+                     unsigned char* take_dev)
+{
+    if (n <= 0) return S2G_OK;
+    S2G_CHECK(n < 2147483647LL, S2G_EINVAL, "healpix far-to-near selection: n = %lld exceeds 2^31-1", n);
+    void *d_keys2, *d_idx, *d_idx2, *d_tmp;
+    S2G_TRY(s2g_scratch(ctx, "hp_keys2", sizeof(unsigned long long) * n, &d_keys2));
+    S2G_TRY(s2g_scratch(ctx, "hp_idx", sizeof(unsigned) * n, &d_idx));
+    S2G_TRY(s2g_scratch(ctx, "hp_idx2", sizeof(unsigned) * n, &d_idx2));
+    const int blocks = (int)((n + 255) / 256);
+    const int ph = s2g_phase_begin(ctx, PH_SORT);
+    k_hp_iota<<<blocks, 256, 0, ctx->stream>>>((unsigned*)d_idx, n);
+    S2G_CUDA(cudaGetLastError());
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, keys_dev, (unsigned long long*)d_keys2, (const unsigned*)d_idx,
+                                    (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream);
+    S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
+    S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, keys_dev, (unsigned long long*)d_keys2, (const unsigned*)d_idx,
+                                             (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream));
+    S2G_CUDA(cudaMemsetAsync(take_dev, 0, (size_t)n, ctx->stream));
+    k_hp_take<<<blocks, 256, 0, ctx->stream>>>((const unsigned*)d_idx2, sel_dev, n, take_dev);
+    S2G_CUDA(cudaGetLastError());
+    s2g_phase_end(ctx, ph);
+    ctx->launches += 9;
+    return S2G_OK;
+}
+
+int s2g_launch_healpix_filtered(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, long long nside,
+                                int kernel, int calc_mean, double* amap, double* wmap, long long* n_selected)
+{
+    if (P.n <= 0) { if (n_selected) *n_selected = 0; return S2G_OK; }
+    const long long n = P.n;
+    void *d_keys, *d_sel, *d_take;
+    S2G_TRY(s2g_scratch(ctx, "hp_keys", sizeof(unsigned long long) * n, &d_keys));
+    S2G_TRY(s2g_scratch(ctx, "hp_sel", (size_t)n, &d_sel));
+    long long nsel = 0;
+    S2G_TRY(s2g_hp_radii(ctx, P, r0, r1, (unsigned long long*)d_keys, (unsigned char*)d_sel, &nsel));
+    if (n_selected) *n_selected = nsel;
     const unsigned char* take = nullptr;
-    if ((long long)h_nsel != n) {
-        S2G_TRY(s2g_scratch(ctx, "hp_keys2", sizeof(unsigned long long) * n, &d_keys2));
-        S2G_TRY(s2g_scratch(ctx, "hp_idx2", sizeof(unsigned) * n, &d_idx2));
+    if (nsel != n) {
         S2G_TRY(s2g_scratch(ctx, "hp_take", (size_t)n, &d_take));
-        ph = s2g_phase_begin(ctx, PH_SORT);
-        size_t sb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned long long*)d_keys, (unsigned long long*)d_keys2,
-                                        (const unsigned*)d_idx, (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream);
-        S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
-        S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned long long*)d_keys,
-                                                 (unsigned long long*)d_keys2, (const unsigned*)d_idx,
-                                                 (unsigned*)d_idx2, (int)n, 0, 64, ctx->stream));
-        S2G_CUDA(cudaMemsetAsync(d_take, 0, (size_t)n, ctx->stream));
-        k_hp_take<<<blocks, 256, 0, ctx->stream>>>((const unsigned*)d_idx2, (const unsigned char*)d_sel, n,
-                                                   (unsigned char*)d_take);
-        S2G_CUDA(cudaGetLastError());
-        s2g_phase_end(ctx, ph);
-        ctx->launches += 8;
+        S2G_TRY(s2g_hp_take_mask(ctx, (const unsigned long long*)d_keys, (const unsigned char*)d_sel, n,
+                                 (unsigned char*)d_take));
         take = (const unsigned char*)d_take;
     }
     return s2g_launch_healpix(ctx, P, nside, kernel, calc_mean, take, amap, wmap);

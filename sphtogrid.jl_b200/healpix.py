@@ -50,16 +50,19 @@ def healpix_deposit(pos, hsml, m, rho, bin_q, weights, Nside, kernel, calc_mean=
 
 
 def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), radius_limits=(0.0, np.inf),
-                Nside=1024, kernel, show_progress=True, output_from_all_workers=False, calc_mean=True, ctx=None):
+                Nside=1024, kernel, show_progress=True, output_from_all_workers=False, calc_mean=True, ctx=None,
+                group=None):
     """Calculate an allsky map from SPH particles.  Returns `(image, weight_image)` in RING order (0-based storage =
-    Julia pixels[i+1]); divide to reduce the image (main.jl:76-77)."""
+    Julia pixels[i+1]); divide to reduce the image (main.jl:76-77).  `group=DeviceGroup(...)` spreads the particle loop
+    over the GPUs of the group (same result: the shell selection is made over all particles, s2g_group_healpix_map)."""
     npix = 12 * int(Nside) ** 2
     if (not calc_mean) and np.sum(Bin_q) == 0:
         return np.zeros(npix), np.zeros(npix)
     pos = _as_pos(Pos)
     if pos.dtype != np.float64:
         raise TypeError("healpix_map requires Float64 inputs (method signatures `where T`, pixel_weights.jl:87-91)")
-    ctx = ctx or default_context()
+    if group is None:
+        ctx = ctx or default_context()
     n = pos.shape[0]
     f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     hs, mm, rr, bq, ww = f(Hsml), f(M), f(Rho), f(Bin_q), f(Weights)
@@ -77,6 +80,12 @@ def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), ra
     pos_out = np.empty_like(pos)
     cen = (C.c_double * 3)(*[float(c) for c in center])
     rl = (C.c_double * 2)(float(radius_limits[0]), float(radius_limits[1]))
+    if group is not None:
+        check(lib().s2g_group_healpix_map(group.handle, ptr(pos), ptr(hs), ptr(mm), ptr(rr), ptr(bq), ptr(ww), n, cen,
+                                          rl, int(Nside), _kernel_id(kernel), int(calc_mean), ptr(pos_out), ptr(amap),
+                                          ptr(wmap), group.new_stats()))
+        pos[...] = pos_out
+        return amap, wmap
     st = _lib.Stats()
     check(lib().s2g_healpix_map(ctx.handle, ptr(pos), ptr(hs), ptr(mm), ptr(rr), ptr(bq), ptr(ww), n, cen, rl,
                                 int(Nside), _kernel_id(kernel), int(calc_mean), ptr(pos_out), ptr(amap), ptr(wmap),

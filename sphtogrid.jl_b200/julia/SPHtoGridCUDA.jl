@@ -268,4 +268,94 @@ function sphmap_projected(pos_in::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; proje
     return out
 end
 
+# ------------------------------------------------------------------------------------------------------------------
+# parallel=true: several GPUs, ONE Julia process (no Distributed workers, no NCCL.jl)
+# ------------------------------------------------------------------------------------------------------------------
+"""
+    DeviceGroup(devices = 0:device_count()-1)
+
+One library context per listed GPU, driven by host threads inside the library (s2g_group_init).  Replaces the
+`addprocs` + `@spawnat` worker pool of the `parallel=true` branch (src/cic_interpolation/cic_interpolation.jl:171-215,
+236-271): `sphmap_parallel` shards the particles with `domain_decomposition` (src/parallel/domain_decomp.jl:7-17),
+every GPU deposits its slice, and `sum(fetch.(futures))` + `reduce_image` happen on the devices over NVLink peer memory.
+"""
+mutable struct DeviceGroup
+    handle::Ptr{Cvoid}
+    devices::Vector{Int32}
+    function DeviceGroup(devices=0:(ccall((:s2g_device_count, LIB), Cint, ()) - 1))
+        devs = Int32.(collect(devices))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:s2g_group_init, LIB), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), h))
+        grp = new(h[], devs)
+        finalizer(g -> ccall((:s2g_group_shutdown, LIB), Cint, (Ptr{Cvoid},), g.handle), grp)
+        return grp
+    end
+end
+
+Base.length(g::DeviceGroup) = length(g.devices)
+
+const _default_group = Ref{Union{Nothing,DeviceGroup}}(nothing)
+default_group() = something(_default_group[], (_default_group[] = DeviceGroup()))
+
+"""
+    sphmap_parallel(Pos, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions, calc_mean,
+                    reduce_image, return_both_maps, group)
+
+Body of `sphMapping(...; parallel=true)` (cic_interpolation.jl:171-215 for 2D, :236-271 for 3D) on all GPUs of `group`
+(s2g_group_sphmap).  Same arguments and result as `sphmap_fused`; `Pos` is recentred in place.
+"""
+function sphmap_parallel(Pos::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions::Int=2,
+                         calc_mean::Bool=false, reduce_image::Bool=true, return_both_maps::Bool=false,
+                         group::DeviceGroup=default_group()) where {T<:Union{Float32,Float64}}
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+    N = length(m)
+    n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
+    n = par_centred.Npixels[1]
+    out = dimensions == 2 ? (return_both_maps ? Matrix{Float64}(undef, n * n, n_images + 1) :
+                                                Array{Float64,3}(undef, n, n, n_images)) :
+                            Array{Float64,3}(undef, n, n, n)
+    shift = Float64.(param.center); half = Float64.(par_centred.halfsize)
+    pos_out = similar(Pos)
+    GC.@preserve Pos hsml m rho bq w out shift half pos_out begin
+        check(ccall((:s2g_group_sphmap, LIB), Cint,
+                    (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Int64, Int32, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Float64, Int64, Int32, Int32,
+                     Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                    group.handle, dimensions, Pos, hsml, m, rho, bq, w, N, n_images,
+                    T == Float32 ? S2G_F32 : S2G_F64, shift, param.periodic, Float64(param.boxsize), half,
+                    Float64(par_centred.len2pix), n, kernel_id(kernel), calc_mean, reduce_image, return_both_maps,
+                    pos_out, out, C_NULL))
+    end
+    Pos .= pos_out
+    return out
+end
+
+"""
+    healpix_map_parallel!(allsky_map, weight_map, Pos, Hsml, M, Rho, Bin_q, Weights; center, radius_limits, Nside,
+                          kernel, calc_mean, group)
+
+`healpix_map_fused!` over all GPUs of `group` (s2g_group_healpix_map); the `sorted[sel]` selection of
+filter_sort_particles (src/healpix_interpolation/filter_particles.jl:33-41) is made over ALL particles, so the maps
+are those of the single-device call.
+"""
+function healpix_map_parallel!(allsky_map, weight_map, Pos::Matrix{Float64}, Hsml::Vector{Float64},
+                               M::Vector{Float64}, Rho::Vector{Float64}, Bin_q::Vector{Float64},
+                               Weights::Vector{Float64}; center::Vector{<:Real}, radius_limits::Vector{<:Real},
+                               Nside::Integer, kernel::AbstractSPHKernel, calc_mean::Bool=true,
+                               group::DeviceGroup=default_group())
+    a, w = allsky_map.pixels, weight_map.pixels
+    cen = Float64.(center); rl = Float64.(radius_limits)
+    pos_out = similar(Pos)
+    GC.@preserve Pos Hsml M Rho Bin_q Weights a w cen rl pos_out begin
+        check(ccall((:s2g_group_healpix_map, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+                     Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+                    group.handle, Pos, Hsml, M, Rho, Bin_q, Weights, length(Hsml), cen, rl, Nside, kernel_id(kernel),
+                    calc_mean, pos_out, a, w, C_NULL))
+    end
+    Pos .= pos_out
+    return allsky_map, weight_map
+end
+
 end # module

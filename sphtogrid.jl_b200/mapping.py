@@ -215,12 +215,14 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
                kernel: AbstractSPHKernel, show_progress: bool = True, parallel: bool = False,
                reduce_image: bool = True, return_both_maps: bool = False, dimensions: int = 2,
                calc_mean: bool = False, stokes: bool = False, sort_z: bool = False, ctx=None, return_stats=False,
-               _projection=None):
+               group=None, _projection=None):
     """Maps the data in `Bin_Quant` to a grid (cic_interpolation.jl:35-273).
 
-    `Pos` is recentred IN PLACE like the reference does.  `parallel=True` shards the particles over the ranks of an
-    initialised torch.distributed process group (one GPU per rank) with `domain_decomposition` and sums the partial
-    flat images with an NCCL all-reduce before the division (`image = sum(fetch.(futures))`, :199/:256)."""
+    `Pos` is recentred IN PLACE like the reference does.  `parallel=True` shards the particles with
+    `domain_decomposition` and sums the partial flat images before the division (`image = sum(fetch.(futures))`,
+    :199/:256): with `group=DeviceGroup(...)` over the GPUs of that group inside this one process (host thread per
+    device, peer-memory sum fused with reduce_image: s2g_group_sphmap), otherwise over the ranks of an initialised
+    torch.distributed process group (one GPU per rank, NCCL all-reduce)."""
     if stokes:
         # cic_interpolation.jl:74-81: back-to-front order, serial.  NB the reference does NOT forward `stokes` to
         # cic_mapping_2D (:152-155), so through sphMapping the RM never rotates anything; reproduced: the map is
@@ -256,6 +258,28 @@ def sphMapping(Pos, HSML, M, Rho, Bin_Quant, Weights=None, RM=None, *, param: ma
             dt, code = _common_dtype(pos, HSML, M, Rho, Bin_Quant, Weights)
             bq, nim = _binq(Bin_Quant, n, dt)
             hs, mm, rr, ww = _prep(HSML, dt), _prep(M, dt), _prep(Rho, dt), _prep(Weights, dt)
+
+    if parallel and group is not None:
+        both = bool(return_both_maps) and dimensions == 2
+        if dimensions == 2:
+            out = np.zeros((npix * npix, nim + 1), order="F") if both else np.zeros((npix, npix, nim), order="F")
+        else:
+            out = np.zeros((npix, npix, npix), order="F")
+        if pos.dtype != dt:
+            # Float32 positions with Float64 fields: recentre first in Float32 (Q2), then map without a further shift
+            center_particles(pos, param, ctx=group.context(0))
+            shift, periodic, boxsize, p_in, p_out = [0, 0, 0], 0, -1.0, _prep(pos, dt), None
+        else:
+            shift, periodic, boxsize, p_in = param.center, int(param.periodic), float(param.boxsize), pos
+            p_out = np.empty_like(pos)
+        gst = group.new_stats()
+        check(lib().s2g_group_sphmap(group.handle, dimensions, ptr(p_in), ptr(hs), ptr(mm), ptr(rr), ptr(bq), ptr(ww), n,
+                                     nim, code, dbl3(shift), periodic, boxsize, dbl3(par.halfsize), float(par.len2pix),
+                                     npix, kid, int(calc_mean), int(bool(reduce_image)), int(both), ptr(p_out), ptr(out),
+                                     gst))
+        if p_out is not None:
+            pos[...] = p_out
+        return (out, [g.asdict() for g in gst]) if return_stats else out
 
     if parallel:
         from .distributed import sph_mapping_sharded
