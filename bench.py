@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("S2G_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--strategy", default="auto", choices=["auto", "scatter", "gather"])
+    ap.add_argument("--accum", default="f64", choices=["f64", "f32"],
+                    help="f32: the optional FP32-accumulate mode of the 2D gather kernel (1e-5 bar); not the headline")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -214,6 +216,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = s2g.Context(local_rank, strategy=args.strategy)
+    if args.accum != "f64":
+        ctx.set_accumulate_mode(args.accum)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
@@ -394,9 +398,11 @@ def main():
                             "sample": f"first {sample} particles of the same stream, full-size image, {dt:.1f} s"}
         line = {"metric": "Mparticles/s mapped", "value": value, "unit": "Mparticles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64" if args.accum == "f64" else "f32 partial sums in k_gather2d, f64 elsewhere (1e-5 mode)",
+                "data": "synthetic",
                 "config": {"workload": wl["desc"], "particles": n_total, "npix": npix, "kernel": wl["kernel"],
-                           "strategy": args.strategy, "l2": "inputs (%.2f GB/rank) larger than L2" % (n_loc * 64 / 1e9),
+                           "strategy": args.strategy, "accumulate": args.accum, "l2": "inputs (%.2f GB/rank) larger than L2" % (n_loc * 64 / 1e9),
                            "mapped_particles": n_mapped, "pairs": pairs,
                            "footprint_pixels_all_ranks": fpx_all, "touched_pixels_all_ranks": touched_all},
                 "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches * args.steps,

@@ -51,7 +51,7 @@ typedef enum {
     S2G_EINVAL = -1,       /* bad argument */
     S2G_ECUDA = -2,        /* CUDA runtime error / no device */
     S2G_ENOMEM = -3,       /* device or host allocation failed */
-    S2G_EUNSUPPORTED = -4, /* reserved (an fp32-accumulate mode is not built) */
+    S2G_EUNSUPPORTED = -4, /* reserved */
     S2G_EINTERNAL = -5
 } s2g_status;
 
@@ -73,6 +73,14 @@ typedef enum {
     S2G_STRATEGY_SCATTER = 1, /* warp-per-particle, red.global.add.f64           */
     S2G_STRATEGY_GATHER = 2   /* tile-owning CTAs, register accumulators, no atomics */
 } s2g_strategy;
+
+/* arithmetic of the per-pixel inner loop (north_star: FP64 mode to 1e-10, optional FP32-accumulate mode to 1e-5) */
+typedef enum {
+    S2G_ACCUM_F64 = 0, /* default: everything in FP64                                                       */
+    S2G_ACCUM_F32 = 1  /* 2D tile-gather kernel: per-pixel kernel evaluation and per-batch partial sums in
+                          FP32, folded into FP64 accumulators every 256 particles; footprints, pass A
+                          (normalisation), the scatter kernel, 3D, HEALPix and the stencils stay FP64           */
+} s2g_accumulate_mode;
 
 typedef struct s2g_ctx s2g_ctx;
 
@@ -109,6 +117,9 @@ S2G_API int s2g_set_strategy(s2g_ctx* ctx, int strategy /* s2g_strategy */);
  * equals h^2 * ∫w(u) 2πu du to better than 5e-12 relative (tools/analytic_norm_study.py) and the closed form is
  * used by default.  on != 0 forces the numerical sum for every particle. */
 S2G_API int s2g_set_exact_norm(s2g_ctx* ctx, int on);
+/* optional FP32-accumulate mode (s2g_accumulate_mode); maps then agree with the FP64 result to 1e-5 per pixel
+ * (plus 1e-9 of the plane maximum for pixels fed only by kernel-rim contributions). */
+S2G_API int s2g_set_accumulate_mode(s2g_ctx* ctx, int mode /* s2g_accumulate_mode */);
 S2G_API int s2g_get_stats(s2g_ctx* ctx, s2g_stats* out);
 /* pinned host buffers for the end-to-end path */
 S2G_API int s2g_host_alloc(void** out, uint64_t bytes);

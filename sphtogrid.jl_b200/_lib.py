@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 S2G_OK, S2G_EINVAL, S2G_ECUDA, S2G_ENOMEM, S2G_EUNSUPPORTED, S2G_EINTERNAL = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1
 STRATEGY = {"auto": 0, "scatter": 1, "gather": 2}
+ACCUMULATE = {"f64": 0, "f32": 1}
 
 
 class S2GError(RuntimeError):
@@ -62,6 +63,7 @@ _SIGS = {
     "s2g_set_stream": (C.c_int, [_vp, _vp]),
     "s2g_set_strategy": (C.c_int, [_vp, C.c_int]),
     "s2g_set_exact_norm": (C.c_int, [_vp, C.c_int]),
+    "s2g_set_accumulate_mode": (C.c_int, [_vp, C.c_int]),
     "s2g_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "s2g_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "s2g_host_free": (C.c_int, [_vp]),
@@ -178,6 +180,10 @@ class Context:
 
     def set_exact_norm(self, on: bool):
         check(lib().s2g_set_exact_norm(self.handle, int(bool(on))))
+
+    def set_accumulate_mode(self, mode: str):
+        """"f64" (default, parity bar 1e-10) or "f32" (FP32 partial sums in the 2D tile-gather kernel, bar 1e-5)."""
+        check(lib().s2g_set_accumulate_mode(self.handle, ACCUMULATE[mode]))
 
     def set_stream(self, cuda_stream: int):
         check(lib().s2g_set_stream(self.handle, _vp(int(cuda_stream))))

@@ -118,6 +118,15 @@ extern "C" int s2g_set_exact_norm(s2g_ctx* ctx, int on)
     return S2G_OK;
 }
 
+extern "C" int s2g_set_accumulate_mode(s2g_ctx* ctx, int mode)
+{
+    S2G_CHECK(ctx != nullptr, S2G_EINVAL, "s2g_set_accumulate_mode: ctx is NULL");
+    S2G_CHECK(mode == S2G_ACCUM_F64 || mode == S2G_ACCUM_F32, S2G_EINVAL,
+              "s2g_set_accumulate_mode: mode must be 0 (FP64) or 1 (FP32 partial sums)");
+    ctx->accum_f32 = mode == S2G_ACCUM_F32 ? 1 : 0;
+    return S2G_OK;
+}
+
 int s2g_phase_begin(s2g_ctx* ctx, int phase)
 {
     if (ctx->timers_used == ctx->timers.size()) {

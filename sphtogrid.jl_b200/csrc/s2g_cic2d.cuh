@@ -144,6 +144,53 @@ __device__ __forceinline__ double select_or_zero(bool flag, double v)
     return r;
 }
 
+// ---- FP32-accumulate mode (s2g_set_accumulate_mode): the same shape functions in single precision.
+// t = 1 - sqrt(s), sqrt from the MUFU.RSQ seed + one Newton step; callers keep s >= 1e-30 and mask s >= 1.
+template <int KID>
+__device__ __forceinline__ float shape_tf(float t)
+{
+    if (KID == S2G_KERNEL_CUBIC) {
+        const float a = fmaf(fmaf(fmaf(-6.0f, t, 12.0f), t, -6.0f), t, 1.0f), b = 2.0f * (t * t * t);
+        return t > 0.5f ? a : b;
+    } else if (KID == S2G_KERNEL_QUINTIC) {
+        const float b = fmaxf(t - 1.0f / 3.0f, 0.0f), c = fmaxf(t - 2.0f / 3.0f, 0.0f);
+        const float a2 = t * t, b2 = b * b, c2 = c * c;
+        return fmaf(15.0f * c, c2 * c2, fmaf(-6.0f * b, b2 * b2, a2 * a2 * t));
+    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
+        const float t2 = t * t;
+        return (t2 * t2) * fmaf(-4.0f, t, 5.0f);
+    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
+        const float t2 = t * t;
+        return (t2 * t2 * t2) * fmaf(fmaf(35.0f / 3.0f, t, -88.0f / 3.0f), t, 56.0f / 3.0f);
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        const float t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4) * fmaf(fmaf(fmaf(-32.0f, t, 121.0f), t, -154.0f), t, 66.0f);
+    } else {
+        const float t2 = t * t, t4 = t2 * t2, u = 1.0f - t;
+        return (t4 * t4 * t2) * fmaf(fmaf(fmaf(fmaf(429.0f, u, 450.0f), u, 210.0f), u, 50.0f), u, 5.0f);
+    }
+}
+
+template <int KID>
+__device__ __forceinline__ float shape_sf(float s)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+    const float sy = s * y;                        // ~sqrt(s), 2 ulp
+    const float e = fmaf(-sy, y, 1.0f);            // 1 - s*y^2
+    const float r = fmaf(0.5f * sy, e, sy);        // one Newton step on sqrt(s): removes the seed's bias
+    return shape_tf<KID>(1.0f - r);
+}
+
+__device__ __forceinline__ float select_or_zero_f(bool flag, float v)
+{
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tselp.f32 %0, %1, 0f00000000, p;\n\t}"
+        : "=f"(r)
+        : "f"(v), "r"((int)flag));
+    return r;
+}
+
 __device__ __forceinline__ bool nonzero_bits(double v)
 {
     return ((__double2hiint(v) & 0x7fffffff) | __double2loint(v)) != 0;

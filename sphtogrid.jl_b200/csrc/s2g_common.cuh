@@ -52,6 +52,7 @@ struct s2g_ctx {
     bool own_stream = true;
     int strategy = S2G_STRATEGY_AUTO;
     int exact_norm = 0;  // 1: always sum pass A numerically (never use the closed-form kernel integral)
+    int accum_f32 = 0;   // 1: FP32-accumulate mode of the 2D tile-gather kernel (bar 1e-5 instead of 1e-10)
     s2g_stats stats{};
     long long host_pairs = 0;  // (tile,particle) pairs of the gather path, counted on the host
     std::map<std::string, s2g_buffer> pool;  // named scratch buffers, grow-only

@@ -317,7 +317,11 @@ __global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict_
 // Lane layout: a warp covers 16 columns x 2 interleaved rows (half-warp rows halve the idle lanes at the two ends
 // of each chord of the kernel disc compared with 32-wide rows); warp w: column group w&3, row block w>>2;
 // thread rows: i = i0 + (w>>2)*2*RPT + 2*r + (lane>>4), r = 0..RPT-1.
-template <int KID>
+// F32 = FP32-accumulate mode (s2g_set_accumulate_mode): the per-(record, thread) preamble stays FP64 (tile-relative
+// coordinates in units of h, so the conversion to float costs 6e-8 of a quantity of order one), the per-pixel chain
+// (s, 1 - sqrt(s), polynomial, two FMAs) runs in FP32, and the FP32 partial sums are folded into the FP64 register
+// accumulators after every batch of 256 records: per-pixel relative error ~1e-6 (bar of the mode: 1e-5).
+template <int KID, bool F32>
 __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
                                                      const unsigned* __restrict__ tile_beg,
                                                      const unsigned* __restrict__ tile_end,
@@ -365,8 +369,11 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
         const double jd = (double)j, id0 = (double)ibase;
 
         double acc_w[RPT], acc_q[RPT];
+        float facc_w[F32 ? RPT : 1], facc_q[F32 ? RPT : 1];  // FP32 partial sums of the current batch
 #pragma unroll
         for (int r = 0; r < RPT; ++r) { acc_w[r] = 0.0; acc_q[r] = 0.0; }
+#pragma unroll
+        for (int r = 0; r < (F32 ? RPT : 1); ++r) { facc_w[r] = 0.0f; facc_q[r] = 0.0f; }
 
         for (unsigned b = wb; b < we; b += BATCH) {
             const int nb = (int)min((unsigned)BATCH, we - b);
@@ -393,6 +400,38 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 const double dyanq = dyan * s_q[e];
                 const double xb = center_dist(g.x, id0) * hinv;  // a of this thread's first row
                 const double hinv2 = hinv + hinv;
+                if constexpr (F32) {
+                    const float b2f = fmaxf((float)b2, 1e-30f), xbf = (float)xb, hinv2f = (float)hinv2;
+                    const float dyanf = (float)dyan, dyanqf = (float)dyanq;
+                    const float dxlo = (float)g.dx_lo, dxhi = (float)g.dx_hi;
+#pragma unroll
+                    for (int r4 = 0; r4 < RPT; r4 += 4) {
+                        const int g_lo = wbase + 2 * r4, g_hi = g_lo + 7;
+                        if (g_lo > rhi || g_hi < rlo) continue;  // uniform
+                        float sf[4];
+                        bool in[4];
+                        bool any_in = false;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = ibase + 2 * (r4 + k);
+                            const float a = fmaf(-(float)(r4 + k), hinv2f, xbf);
+                            sf[k] = fmaf(a, a, b2f);
+                            in[k] = live && (sf[k] < 1.0f) && (i >= g.iMin) && (i <= g.iMax);
+                            any_in = any_in || in[k];
+                        }
+                        if (!__any_sync(0xffffffffu, any_in)) continue;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = ibase + 2 * (r4 + k);
+                            const float dx = (i == g.iMin) ? dxlo : ((i == g.iMax) ? dxhi : 1.0f);
+                            const float wk = select_or_zero_f(in[k], shape_sf<KID>(sf[k]) * dx);
+                            facc_w[r4 + k] = fmaf(wk, dyanf, facc_w[r4 + k]);
+                            facc_q[r4 + k] = fmaf(wk, dyanqf, facc_q[r4 + k]);
+                            touched += (in[k] && dx != 0.0f) ? 1u : 0u;
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int r4 = 0; r4 < RPT; r4 += 4) {
                     const int g_lo = wbase + 2 * r4, g_hi = g_lo + 7;  // rows of this group (both parities)
@@ -437,6 +476,13 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                             touched += (in[k] && nonzero_bits(dx)) ? 1u : 0u;
                         }
                     }
+                }
+            }
+            if constexpr (F32) {  // fold the batch's FP32 partial sums into the FP64 accumulators
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    acc_w[r] += (double)facc_w[r]; facc_w[r] = 0.0f;
+                    acc_q[r] += (double)facc_q[r]; facc_q[r] = 0.0f;
                 }
             }
         }
@@ -491,9 +537,16 @@ int launch_gather(s2g_ctx* ctx, const GRec* recs, const unsigned* vals, const un
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * 3);
-    k_gather2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles, ntile_j,
-                                                            total_chunks, P.binq, P.in_dtype, G.n_images, image_k,
-                                                            G.npix, image, ctx->d_counters);
+    if (ctx->accum_f32)
+        k_gather2d<KID, true><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles,
+                                                                      ntile_j, total_chunks, P.binq, P.in_dtype,
+                                                                      G.n_images, image_k, G.npix, image,
+                                                                      ctx->d_counters);
+    else
+        k_gather2d<KID, false><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin,
+                                                                       ntiles, ntile_j, total_chunks, P.binq, P.in_dtype,
+                                                                       G.n_images, image_k, G.npix, image,
+                                                                       ctx->d_counters);
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
 }
