@@ -144,33 +144,36 @@ __device__ __forceinline__ double select_or_zero(bool flag, double v)
     return r;
 }
 
-// ---- FP32-accumulate mode (s2g_set_accumulate_mode): the same shape functions in single precision.
-// t = 1 - sqrt(s), sqrt from the MUFU.RSQ seed + one Newton step; callers keep s >= 1e-30 and mask s >= 1.
+// ---- FP32-accumulate mode (s2g_set_accumulate_mode): the shape functions in single precision, as functions of
+// u = sqrt(s) and t = 1 - u.  The Wendland polynomial factors are kept in their u form here (all coefficients
+// positive): the t-expanded forms of the FP64 path cancel ~300:1 near t = 1, which costs nothing at 1e-16 but would
+// cost 2e-5 at FP32's 6e-8.
 template <int KID>
-__device__ __forceinline__ float shape_tf(float t)
+__device__ __forceinline__ float shape_uf(float u, float t)
 {
     if (KID == S2G_KERNEL_CUBIC) {
-        const float a = fmaf(fmaf(fmaf(-6.0f, t, 12.0f), t, -6.0f), t, 1.0f), b = 2.0f * (t * t * t);
-        return t > 0.5f ? a : b;
+        const float a = fmaf(6.0f * (u - 1.0f), u * u, 1.0f), b = 2.0f * (t * t * t);
+        return u < 0.5f ? a : b;
     } else if (KID == S2G_KERNEL_QUINTIC) {
         const float b = fmaxf(t - 1.0f / 3.0f, 0.0f), c = fmaxf(t - 2.0f / 3.0f, 0.0f);
         const float a2 = t * t, b2 = b * b, c2 = c * c;
         return fmaf(15.0f * c, c2 * c2, fmaf(-6.0f * b, b2 * b2, a2 * a2 * t));
     } else if (KID == S2G_KERNEL_WENDLAND_C2) {
         const float t2 = t * t;
-        return (t2 * t2) * fmaf(-4.0f, t, 5.0f);
+        return (t2 * t2) * fmaf(4.0f, u, 1.0f);
     } else if (KID == S2G_KERNEL_WENDLAND_C4) {
         const float t2 = t * t;
-        return (t2 * t2 * t2) * fmaf(fmaf(35.0f / 3.0f, t, -88.0f / 3.0f), t, 56.0f / 3.0f);
+        return (t2 * t2 * t2) * fmaf(fmaf(35.0f / 3.0f, u, 6.0f), u, 1.0f);
     } else if (KID == S2G_KERNEL_WENDLAND_C6) {
         const float t2 = t * t, t4 = t2 * t2;
-        return (t4 * t4) * fmaf(fmaf(fmaf(-32.0f, t, 121.0f), t, -154.0f), t, 66.0f);
+        return (t4 * t4) * fmaf(fmaf(fmaf(32.0f, u, 25.0f), u, 8.0f), u, 1.0f);
     } else {
-        const float t2 = t * t, t4 = t2 * t2, u = 1.0f - t;
+        const float t2 = t * t, t4 = t2 * t2;
         return (t4 * t4 * t2) * fmaf(fmaf(fmaf(fmaf(429.0f, u, 450.0f), u, 210.0f), u, 50.0f), u, 5.0f);
     }
 }
 
+// w(sqrt(s)) for 1e-30 <= s < 1 (garbage for s >= 1: mask it); sqrt from the MUFU.RSQ seed + one Newton step
 template <int KID>
 __device__ __forceinline__ float shape_sf(float s)
 {
@@ -178,8 +181,8 @@ __device__ __forceinline__ float shape_sf(float s)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
     const float sy = s * y;                        // ~sqrt(s), 2 ulp
     const float e = fmaf(-sy, y, 1.0f);            // 1 - s*y^2
-    const float r = fmaf(0.5f * sy, e, sy);        // one Newton step on sqrt(s): removes the seed's bias
-    return shape_tf<KID>(1.0f - r);
+    const float u = fmaf(0.5f * sy, e, sy);        // one Newton step on sqrt(s): removes the seed's bias
+    return shape_uf<KID>(u, 1.0f - u);
 }
 
 __device__ __forceinline__ float select_or_zero_f(bool flag, float v)

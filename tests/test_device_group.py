@@ -92,8 +92,7 @@ def test_group_sphmapping_2d_equals_serial_and_oracle(s2g, oracle, no_p2p, monke
         assert len(stats) == len(devs)
         assert sum(s["n_in"] for s in stats) == pos.shape[0]
         assert [s["n_in"] for s in stats] == [b - a for a, b in s2g.domain_decomposition(pos.shape[0], len(devs))]
-        if len(devs) == 1:
-            assert np.array_equal(got, serial)
+        # (not bit-equal even for one device: the scatter kernel's red.add order differs from run to run)
         assert_parity(got, serial, rtol=1e-12, what=f"group {devs} vs serial")
         assert_parity(got, ref, what=f"group {devs} vs oracle")
         grp.close()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """One-process multi-GPU path (DeviceGroup, s2g_group_sphmap) timed end to end from host arrays against the
-single-context call on the same inputs: 4 Mi particles of the c2 stream -> 2048^2, WendlandC6, calc_mean T map.
+single-context call on the same inputs: S2G_GROUP_BENCH_N (4 Mi) particles of the c2 stream -> S2G_GROUP_BENCH_NPIX
+(2048)^2, WendlandC6, calc_mean T map; times are wall clock around the public call, host numpy arrays in and out.
 With one GPU the group lists device 0 twice (functional check of sharding + peer sum; no speed-up expected)."""
 import json
 import os
@@ -19,7 +20,8 @@ nd = s2g.lib().s2g_device_count()
 n = int(os.environ.get("S2G_GROUP_BENCH_N", 4 << 20))
 wl = dict(bench.WORKLOADS["c2"])
 pos, hsml, m, rho, temp = bench.host_particles(wl, n)
-par = s2g.mappingParameters(center=[0.5, 0.5, 0.5], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=2048)
+npix = int(os.environ.get("S2G_GROUP_BENCH_NPIX", 2048))
+par = s2g.mappingParameters(center=[0.5, 0.5, 0.5], x_size=1.0, y_size=1.0, z_size=1.0, Npixels=npix)
 kern = s2g.WendlandC6(2)
 
 
@@ -39,7 +41,7 @@ devs = list(range(nd)) if nd > 1 else [0, 0]
 grp = s2g.DeviceGroup(devs)
 tg, (b, stg) = run(parallel=True, group=grp)
 err = float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-300)))
-print(json.dumps({"particles": n, "npix": 2048, "devices": devs, "peer_access": grp.peer_access,
+print(json.dumps({"particles": n, "npix": npix, "devices": devs, "peer_access": grp.peer_access,
                   "single_ms": t1 * 1e3, "group_ms": tg * 1e3, "max_rel_diff_group_vs_single": err,
                   "single_stats_ms": {k: st1[k] for k in ("ms_h2d", "ms_compute", "ms_epilogue", "ms_d2h")},
                   "group_stats_ms": [{k: s[k] for k in ("ms_h2d", "ms_compute", "ms_epilogue", "ms_d2h")} for s in stg]}))
