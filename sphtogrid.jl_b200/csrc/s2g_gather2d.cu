@@ -34,7 +34,7 @@ struct __align__(16) GRec {
     double dy_lo, dy_hi;         //                     first / last column
     double h;
     int p;                       // particle index (for the per-image quantity)
-    int pad;
+    int f32_ok;                  // FP32-accumulate mode may evaluate this particle in single precision (k_norm2d)
 };
 
 // integral of the kernel shape over the unit disc, ∫ w(u) 2πu du = 1 / norm_2D(kernel)
@@ -237,7 +237,12 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
         g.x = r.x; g.y = r.y; g.h = r.h; g.hinv = r.hinv;
         g.dx_lo = dx_lo; g.dx_hi = dx_hi; g.dy_lo = dy_lo; g.dy_hi = dy_hi;
         g.iMin = r.iMin; g.iMax = r.iMax; g.jMin = r.jMin; g.jMax = r.jMax;
-        g.p = (int)p; g.pad = 0;
+        g.p = (int)p;
+        // FP32-accumulate mode: a footprint that keeps less than half of the kernel integral inside the image is
+        // renormalised by the reference to carry the particle's whole weight anyway, so contributions from the kernel
+        // rim (1-u)^k, whose relative error in single precision is ~k*6e-8/(1-u), can dominate a border pixel (measured:
+        // 2.8e-5 on a pixel at u = 0.983).  Those particles keep the FP64 chain.
+        g.f32_ok = (sw >= 0.5 * closed) ? 1 : 0;
         unsigned np = 0;
         const double an_probe = (r.area / sw) * r.w * r.dz;
         if (sw == 0.0 || !isfinite(an_probe)) {
@@ -320,7 +325,8 @@ __global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict_
 // F32 = FP32-accumulate mode (s2g_set_accumulate_mode): the per-(record, thread) preamble stays FP64 (tile-relative
 // coordinates in units of h, so the conversion to float costs 6e-8 of a quantity of order one), the per-pixel chain
 // (s, 1 - sqrt(s), polynomial, two FMAs) runs in FP32, and the FP32 partial sums are folded into the FP64 register
-// accumulators after every batch of 256 records: per-pixel relative error ~1e-6 (bar of the mode: 1e-5).
+// accumulators after every batch of 256 records: per-pixel relative error ~1e-7 median, 1e-6 worst (bar of the mode:
+// 1e-5).  Records flagged !f32_ok (most of the kernel clipped away by the image border) take the FP64 chain.
 template <int KID, bool F32>
 __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
                                                      const unsigned* __restrict__ tile_beg,
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 const double dyanq = dyan * s_q[e];
                 const double xb = center_dist(g.x, id0) * hinv;  // a of this thread's first row
                 const double hinv2 = hinv + hinv;
-                if constexpr (F32) {
+                if (F32 && g.f32_ok) {
                     const float b2f = fmaxf((float)b2, 1e-30f), xbf = (float)xb, hinv2f = (float)hinv2;
                     const float dyanf = (float)dyan, dyanqf = (float)dyanq;
                     const float dxlo = (float)g.dx_lo, dxhi = (float)g.dx_hi;
