@@ -130,6 +130,45 @@ __device__ __forceinline__ double shape_s(double s)
     return shape_t<KID>(fma(-s, rsqrt_fast(s), 1.0));
 }
 
+// ---- one-constant-per-step forms for the tile-gather inner loop.  A DFMA takes ONE immediate; a Horner step with
+// two literal constants (fma(-32, t, 121)) makes ptxas re-materialise the second one with two IMAD.MOVs per group of
+// pixels.  Dividing the polynomial factor by its leading coefficient where that is a power of two turns the first
+// step into a DADD with an immediate and leaves every other step with a single immediate;
+//     shape_t<KID>(t) == shape_scale<KID>() * shape_t_scaled<KID>(t)   bit for bit
+// (scaling by 2^k commutes with every rounding), and the caller folds shape_scale into area_norm once per record.
+template <int KID>
+__host__ __device__ constexpr double shape_scale()
+{
+    return KID == S2G_KERNEL_WENDLAND_C6 ? 32.0 : (KID == S2G_KERNEL_WENDLAND_C2 ? 4.0 : 1.0);
+}
+
+template <int KID>
+__device__ __forceinline__ double shape_t_scaled(double t)
+{
+    if (KID == S2G_KERNEL_WENDLAND_C2) {
+        const double t2 = t * t;
+        return (t2 * t2) * (1.25 - t);
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        const double t2 = t * t, t4 = t2 * t2;
+        return (t4 * t4) * fma(fma(3.78125 - t, t, -4.8125), t, 2.0625);
+    } else {
+        return shape_t<KID>(t);
+    }
+}
+
+template <int KID>
+__device__ __forceinline__ double shape_s_scaled(double s)
+{
+    return shape_t_scaled<KID>(fma(-s, rsqrt_fast(s), 1.0));
+}
+
+// ++counter if flag, as ONE predicated add (the C++ form compiles to SEL + IADD3; the tile-gather kernel is close to
+// issue bound — FP64 is only 52 % of its instructions — so per-pixel integer instructions count)
+__device__ __forceinline__ void count_if(bool flag, unsigned& counter)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(counter) : "r"((int)flag));
+}
+
 // s < 1.0 for s > 0 (or NaN -> false), decided on the integer pipe from the high word: 1.0 = 0x3ff00000'00000000
 __device__ __forceinline__ bool below_one(double s) { return __double2hiint(s) < 0x3ff00000; }
 
@@ -183,6 +222,59 @@ __device__ __forceinline__ float shape_sf(float s)
     const float e = fmaf(-sy, y, 1.0f);            // 1 - s*y^2
     const float u = fmaf(0.5f * sy, e, sy);        // one Newton step on sqrt(s): removes the seed's bias
     return shape_uf<KID>(u, 1.0f - u);
+}
+
+// ---- the same in packed single precision (Blackwell FFMA2 / FMUL2 / FADD2: one instruction, two pixels).  The
+// tile-gather kernel is close to issue bound, so in FP32-accumulate mode the instruction count per pixel, not the FP32
+// rate, sets the speed: two rows of a thread's column share every arithmetic instruction of the chain.
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+template <int KID>
+__device__ __forceinline__ float2 shape_uf2(float2 u, float2 t)
+{
+    if (KID == S2G_KERNEL_CUBIC) {
+        // u < 0.5: 1 + 6(u-1)u^2 = 1 - 6 u^2 t ; else 2 t^3
+        const float2 a = __ffma2_rn(__fmul2_rn(f2(-6.0f), t), __fmul2_rn(u, u), f2(1.0f));
+        const float2 b = __fmul2_rn(__fmul2_rn(f2(2.0f), t), __fmul2_rn(t, t));
+        return make_float2(u.x < 0.5f ? a.x : b.x, u.y < 0.5f ? a.y : b.y);
+    } else if (KID == S2G_KERNEL_QUINTIC) {
+        const float2 b = make_float2(fmaxf(t.x - 1.0f / 3.0f, 0.0f), fmaxf(t.y - 1.0f / 3.0f, 0.0f));
+        const float2 c = make_float2(fmaxf(t.x - 2.0f / 3.0f, 0.0f), fmaxf(t.y - 2.0f / 3.0f, 0.0f));
+        const float2 a2 = __fmul2_rn(t, t), b2 = __fmul2_rn(b, b), c2 = __fmul2_rn(c, c);
+        return __ffma2_rn(__fmul2_rn(f2(15.0f), c), __fmul2_rn(c2, c2),
+                          __ffma2_rn(__fmul2_rn(f2(-6.0f), b), __fmul2_rn(b2, b2), __fmul2_rn(__fmul2_rn(a2, a2), t)));
+    } else if (KID == S2G_KERNEL_WENDLAND_C2) {
+        const float2 t2 = __fmul2_rn(t, t);
+        return __fmul2_rn(__fmul2_rn(t2, t2), __ffma2_rn(f2(4.0f), u, f2(1.0f)));
+    } else if (KID == S2G_KERNEL_WENDLAND_C4) {
+        const float2 t2 = __fmul2_rn(t, t);
+        return __fmul2_rn(__fmul2_rn(__fmul2_rn(t2, t2), t2),
+                          __ffma2_rn(__ffma2_rn(f2(35.0f / 3.0f), u, f2(6.0f)), u, f2(1.0f)));
+    } else if (KID == S2G_KERNEL_WENDLAND_C6) {
+        const float2 t2 = __fmul2_rn(t, t), t4 = __fmul2_rn(t2, t2);
+        return __fmul2_rn(__fmul2_rn(t4, t4),
+                          __ffma2_rn(__ffma2_rn(__ffma2_rn(f2(32.0f), u, f2(25.0f)), u, f2(8.0f)), u, f2(1.0f)));
+    } else {
+        const float2 t2 = __fmul2_rn(t, t), t4 = __fmul2_rn(t2, t2);
+        return __fmul2_rn(
+            __fmul2_rn(__fmul2_rn(t4, t4), t2),
+            __ffma2_rn(__ffma2_rn(__ffma2_rn(__ffma2_rn(f2(429.0f), u, f2(450.0f)), u, f2(210.0f)), u, f2(50.0f)), u,
+                       f2(5.0f)));
+    }
+}
+
+// w(sqrt(s)) for two pixels, 1e-30 <= s < 1 (garbage for s >= 1: mask it); the two MUFU.RSQ seeds are the only scalar
+// instructions; signs are arranged so that no packed negation is needed (em = s*y^2 - 1 = -e)
+template <int KID>
+__device__ __forceinline__ float2 shape_sf2(float2 s)
+{
+    float2 y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(s.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(s.y));
+    const float2 sy = __fmul2_rn(s, y);                                   // ~sqrt(s)
+    const float2 em = __ffma2_rn(sy, y, f2(-1.0f));                       // s*y^2 - 1
+    const float2 u = __ffma2_rn(__fmul2_rn(sy, f2(-0.5f)), em, sy);       // one Newton step on sqrt(s)
+    return shape_uf2<KID>(u, __ffma2_rn(u, f2(-1.0f), f2(1.0f)));
 }
 
 __device__ __forceinline__ float select_or_zero_f(bool flag, float v)

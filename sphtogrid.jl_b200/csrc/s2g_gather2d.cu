@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
 {
     __shared__ GRec s_rec[BATCH];
     __shared__ double s_q[BATCH];
+    __shared__ float4 s_f[F32 ? BATCH : 1];  // FP32-accumulate mode: (2/h, dx_lo, dx_hi, -) converted once per record
     __shared__ unsigned s_work[3];
 
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
@@ -372,22 +373,56 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
         const int jw0 = j0 + (wq & 3) * 16;   // first column of this warp (uniform)
         const int wbase = i0 + rblk;          // first row of this warp (uniform)
         const int ibase = wbase + rpar;       // first row of this thread; its rows are ibase + 2r
-        const double jd = (double)j, id0 = (double)ibase;
+        // this thread's column / first row centre inside the tile.  Opaque to the compiler on purpose: as plain functions
+        // of threadIdx ptxas re-materialises them for every record (LOP3 + I2F.F64 + DADD, twice) instead of keeping
+        // four registers
+        double jld = (double)jl + 0.5, ild = (double)(rblk + rpar) + 0.5;
+        asm volatile("" : "+d"(jld), "+d"(ild));
 
-        double acc_w[RPT], acc_q[RPT];
-        float facc_w[F32 ? RPT : 1], facc_q[F32 ? RPT : 1];  // FP32 partial sums of the current batch
+        // FP64 chain: in the FP64-only kernel the polynomial factor is scaled by 1/shape_scale (folded into g.an above)
+        auto shape_fp64 = [](double s) { return F32 ? shape_s<KID>(s) : shape_s_scaled<KID>(s); };
+        // FP64 mode: the thread's 8 pixels x 2 planes live in FP64 registers for the whole work item.
+        // FP32-accumulate mode: packed FP32 partial sums of the current batch of 256 records (row pairs), added to the
+        // FP64 image at the end of every batch — no FP64 accumulator registers, which is what lets this variant keep
+        // 3 CTAs/SM; the accumulation error does not grow with the length of a tile's particle list.
+        double acc_w[F32 ? 1 : RPT], acc_q[F32 ? 1 : RPT];
+        float2 facc_w[F32 ? RPT / 2 : 1], facc_q[F32 ? RPT / 2 : 1];
 #pragma unroll
-        for (int r = 0; r < RPT; ++r) { acc_w[r] = 0.0; acc_q[r] = 0.0; }
+        for (int r = 0; r < (F32 ? 1 : RPT); ++r) { acc_w[r] = 0.0; acc_q[r] = 0.0; }
 #pragma unroll
-        for (int r = 0; r < (F32 ? RPT : 1); ++r) { facc_w[r] = 0.0f; facc_q[r] = 0.0f; }
+        for (int r = 0; r < (F32 ? RPT / 2 : 1); ++r) { facc_w[r] = f2(0.0f); facc_q[r] = f2(0.0f); }
+        const long long npl = npix * npix;
+        // one pixel of this thread's column to the image: half-warps write 16 consecutive doubles (128 B) of a row
+        auto flush_px = [&](int i, double w, double q) {
+            // FP32-accumulate mode flushes inside the batch loop: keep the address arithmetic HERE (hoisted out of the
+            // loop as loop-invariant it pins 26 registers for the 16 addresses and spills the rest)
+            if constexpr (F32) asm volatile("" : "+r"(i));
+            if (i < npix && (w != 0.0 || q != 0.0)) {
+                const long long idx = (long long)i * npix + j;
+                if (image_k == 0) red_add(image + npl * n_images + idx, w);
+                red_add(image + npl * image_k + idx, q);
+            }
+        };
 
         for (unsigned b = wb; b < we; b += BATCH) {
             const int nb = (int)min((unsigned)BATCH, we - b);
             __syncthreads();  // previous batch fully consumed
             if (tid < nb) {
-                const GRec g = recs[vals[b + tid]];
+                // the shared-memory copy is made TILE-RELATIVE by the loading thread: x := x - i0, y := y - j0 (exact: a
+                // multiple of ulp(x) that is smaller than x, or a difference of at most h).  The per-(record, thread)
+                // offset is then ONE subtraction of the thread's constant (row + 0.5), a single rounding of the exact
+                // x - i - 0.5 where get_x_dx (cic_shared.jl:73) rounds twice — never further from the exact value.
+                // (Scaling by 1/h BEFORE subtracting the thread's offset saves another instruction but cancels: the
+                // error grows to 64/h ulp, which the kernel rim (1-u)^k amplifies beyond the 1e-10 bar — measured.)
+                //   h := 2/h (row stride of a thread: its rows are two apart);  s_q := area_norm * quantity
+                GRec g = recs[vals[b + tid]];
+                if (!F32) g.an *= shape_scale<KID>();  // exact (power of two), see shape_t_scaled
+                g.x = g.x - (double)i0;
+                g.y = g.y - (double)j0;
+                g.h = g.hinv + g.hinv;
                 s_rec[tid] = g;
-                s_q[tid] = ld_in(binq, (long long)n_images * g.p + image_k, in_dtype);
+                s_q[tid] = g.an * ld_in(binq, (long long)n_images * g.p + image_k, in_dtype);
+                if constexpr (F32) s_f[tid] = make_float4((float)g.h, (float)g.dx_lo, (float)g.dx_hi, 0.0f);
             }
             __syncthreads();
             for (int e = 0; e < nb; ++e) {
@@ -396,44 +431,79 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 const int rlo = max(g.iMin, wbase), rhi = min(g.iMax, wbase + 2 * RPT - 1);
                 if (rlo > rhi || g.jMax < jw0 || g.jMin > jw0 + 15) continue;
                 const double hinv = g.hinv;
-                const double bq = center_dist(g.y, jd) * hinv;
+                const double bq = (g.y - jld) * hinv;
                 const double b2 = fma(bq, bq, 1e-300);  // s > 0 even when a pixel centre sits on the particle
                 const double dy = (j == g.jMin) ? g.dy_lo : ((j == g.jMax) ? g.dy_hi : 1.0);
                 const double dyan = dy * g.an;
                 // pix_weight != 0 test of cic_2D.jl:211 hoisted: wk > 0 inside the disc, so only dy*area_norm decides
                 const bool live = (j >= g.jMin) && (j <= g.jMax) && below_one(b2) && nonzero_bits(dyan);
                 if (!__any_sync(0xffffffffu, live)) continue;
-                const double dyanq = dyan * s_q[e];
-                const double xb = center_dist(g.x, id0) * hinv;  // a of this thread's first row
-                const double hinv2 = hinv + hinv;
+                const double dyanq = dy * s_q[e];
+                const double xb = (g.x - ild) * hinv;  // a of this thread's first row
+                const double hinv2 = g.h;
+                // pixel r of this thread += wk * (dyan, dyanq), FP64 chain (in the FP32-accumulate kernel: the records
+                // whose kernel is mostly clipped away are EVALUATED in FP64; their products join the FP32 partial sums)
+                auto add_px = [&](int r, double wk) {
+                    if constexpr (F32) {
+                        const float pw = (float)(wk * dyan), pq = (float)(wk * dyanq);
+                        if (r & 1) { facc_w[r >> 1].y += pw; facc_q[r >> 1].y += pq; }
+                        else       { facc_w[r >> 1].x += pw; facc_q[r >> 1].x += pq; }
+                    } else {
+                        acc_w[r] = fma(wk, dyan, acc_w[r]);
+                        acc_q[r] = fma(wk, dyanq, acc_q[r]);
+                    }
+                };
                 if (F32 && g.f32_ok) {
-                    const float b2f = fmaxf((float)b2, 1e-30f), xbf = (float)xb, hinv2f = (float)hinv2;
-                    const float dyanf = (float)dyan, dyanqf = (float)dyanq;
-                    const float dxlo = (float)g.dx_lo, dxhi = (float)g.dx_hi;
+                    // two rows per instruction (FFMA2): pairs (r4, r4+1) and (r4+2, r4+3) of each group of four
+                    const float4 gf = s_f[F32 ? e : 0];
+                    const float2 b22 = f2(fmaxf((float)b2, 1e-30f)), xb2 = f2((float)xb), hinv22 = f2(gf.x);
+                    const float2 dyan2 = f2((float)dyan), dyanq2 = f2((float)dyanq);
+                    const float dxlo = gf.y, dxhi = gf.z;
 #pragma unroll
                     for (int r4 = 0; r4 < RPT; r4 += 4) {
                         const int g_lo = wbase + 2 * r4, g_hi = g_lo + 7;
                         if (g_lo > rhi || g_hi < rlo) continue;  // uniform
-                        float sf[4];
-                        bool in[4];
-                        bool any_in = false;
+                        float2 sf[2];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = ibase + 2 * (r4 + k);
-                            const float a = fmaf(-(float)(r4 + k), hinv2f, xbf);
-                            sf[k] = fmaf(a, a, b2f);
-                            in[k] = live && (sf[k] < 1.0f) && (i >= g.iMin) && (i <= g.iMax);
-                            any_in = any_in || in[k];
+                        for (int h = 0; h < 2; ++h) {
+                            const float2 a = __ffma2_rn(make_float2(-(float)(r4 + 2 * h), -(float)(r4 + 2 * h + 1)),
+                                                        hinv22, xb2);
+                            sf[h] = __ffma2_rn(a, a, b22);
                         }
-                        if (!__any_sync(0xffffffffu, any_in)) continue;
+                        bool in[4];
+                        in[0] = live && (sf[0].x < 1.0f); in[1] = live && (sf[0].y < 1.0f);
+                        in[2] = live && (sf[1].x < 1.0f); in[3] = live && (sf[1].y < 1.0f);
+                        if ((g_lo > g.iMin) && (g_hi < g.iMax)) {  // uniform: no first/last row in this group
+                            if (!__any_sync(0xffffffffu, in[0] || in[1] || in[2] || in[3])) continue;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = ibase + 2 * (r4 + k);
-                            const float dx = (i == g.iMin) ? dxlo : ((i == g.iMax) ? dxhi : 1.0f);
-                            const float wk = select_or_zero_f(in[k], shape_sf<KID>(sf[k]) * dx);
-                            facc_w[r4 + k] = fmaf(wk, dyanf, facc_w[r4 + k]);
-                            facc_q[r4 + k] = fmaf(wk, dyanqf, facc_q[r4 + k]);
-                            touched += (in[k] && dx != 0.0f) ? 1u : 0u;
+                            for (int h = 0; h < 2; ++h) {
+                                float2 wk = shape_sf2<KID>(sf[h]);
+                                wk.x = select_or_zero_f(in[2 * h], wk.x);
+                                wk.y = select_or_zero_f(in[2 * h + 1], wk.y);
+                                facc_w[(r4 >> 1) + h] = __ffma2_rn(wk, dyan2, facc_w[(r4 >> 1) + h]);
+                                facc_q[(r4 >> 1) + h] = __ffma2_rn(wk, dyanq2, facc_q[(r4 >> 1) + h]);
+                                count_if(in[2 * h], touched);
+                                count_if(in[2 * h + 1], touched);
+                            }
+                        } else {
+                            float dx[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int i = ibase + 2 * (r4 + k);
+                                in[k] = in[k] && (i >= g.iMin) && (i <= g.iMax);
+                                dx[k] = (i == g.iMin) ? dxlo : ((i == g.iMax) ? dxhi : 1.0f);
+                            }
+                            if (!__any_sync(0xffffffffu, in[0] || in[1] || in[2] || in[3])) continue;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                float2 wk = __fmul2_rn(shape_sf2<KID>(sf[h]), make_float2(dx[2 * h], dx[2 * h + 1]));
+                                wk.x = select_or_zero_f(in[2 * h], wk.x);
+                                wk.y = select_or_zero_f(in[2 * h + 1], wk.y);
+                                facc_w[(r4 >> 1) + h] = __ffma2_rn(wk, dyan2, facc_w[(r4 >> 1) + h]);
+                                facc_q[(r4 >> 1) + h] = __ffma2_rn(wk, dyanq2, facc_q[(r4 >> 1) + h]);
+                                count_if(in[2 * h] && dx[2 * h] != 0.0f, touched);
+                                count_if(in[2 * h + 1] && dx[2 * h + 1] != 0.0f, touched);
+                            }
                         }
                     }
                     continue;
@@ -457,10 +527,8 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                         if (!__any_sync(0xffffffffu, any_in)) continue;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const double wk = select_or_zero(in[k], shape_s<KID>(s[k]));
-                            acc_w[r4 + k] = fma(wk, dyan, acc_w[r4 + k]);
-                            acc_q[r4 + k] = fma(wk, dyanq, acc_q[r4 + k]);
-                            touched += in[k] ? 1u : 0u;
+                            add_px(r4 + k, select_or_zero(in[k], shape_fp64(s[k])));
+                            count_if(in[k], touched);
                         }
                     } else {
 #pragma unroll
@@ -476,33 +544,28 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                         for (int k = 0; k < 4; ++k) {
                             const int i = ibase + 2 * (r4 + k);
                             const double dx = (i == g.iMin) ? g.dx_lo : ((i == g.iMax) ? g.dx_hi : 1.0);
-                            const double wk = select_or_zero(in[k], shape_s<KID>(s[k]) * dx);
-                            acc_w[r4 + k] = fma(wk, dyan, acc_w[r4 + k]);
-                            acc_q[r4 + k] = fma(wk, dyanq, acc_q[r4 + k]);
-                            touched += (in[k] && nonzero_bits(dx)) ? 1u : 0u;
+                            add_px(r4 + k, select_or_zero(in[k], shape_fp64(s[k]) * dx));
+                            count_if(in[k] && nonzero_bits(dx), touched);
                         }
                     }
                 }
             }
-            if constexpr (F32) {  // fold the batch's FP32 partial sums into the FP64 accumulators
+            if constexpr (F32) {  // the batch's FP32 partial sums join the FP64 image
+                if (j < npix) {
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    acc_w[r] += (double)facc_w[r]; facc_w[r] = 0.0f;
-                    acc_q[r] += (double)facc_q[r]; facc_q[r] = 0.0f;
+                    for (int r = 0; r < RPT / 2; ++r) {
+                        flush_px(ibase + 4 * r, (double)facc_w[r].x, (double)facc_q[r].x);
+                        flush_px(ibase + 4 * r + 2, (double)facc_w[r].y, (double)facc_q[r].y);
+                    }
                 }
+#pragma unroll
+                for (int r = 0; r < RPT / 2; ++r) { facc_w[r] = f2(0.0f); facc_q[r] = f2(0.0f); }
             }
         }
-        // flush: each half-warp writes 16 consecutive doubles (128 B) of one image row
-        const long long npl = npix * npix;
-        if (j < npix) {
+        if constexpr (!F32) {  // one flush per work item
+            if (j < npix) {
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) {
-                const int i = ibase + 2 * r;
-                if (i < npix && (acc_w[r] != 0.0 || acc_q[r] != 0.0)) {
-                    const long long idx = (long long)i * npix + j;
-                    if (image_k == 0) red_add(image + npl * n_images + idx, acc_w[r]);
-                    red_add(image + npl * image_k + idx, acc_q[r]);
-                }
+                for (int r = 0; r < RPT; ++r) flush_px(ibase + 2 * r, acc_w[r], acc_q[r]);
             }
         }
         if (image_k == 0 && touched > 0x7f000000u) {  // keep the 32-bit per-thread counter from wrapping
