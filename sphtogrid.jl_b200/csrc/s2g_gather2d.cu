@@ -20,9 +20,23 @@ int s2g_launch_scatter_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
 
 namespace {
 
-constexpr int TILE_W = 64;     // tile width  (j, the contiguous image axis): 2 warps side by side
-constexpr int RPT = 8;         // rows per thread
-constexpr int TILE_H = 4 * RPT;  // tile height (i): 4 row groups of RPT rows -> 256 threads
+// CTA geometry of k_gather2d: a warp covers 16 columns x 16 rows (2 interleaved rows per pass, RPT rows per thread);
+// a CTA is NCG warps side by side (columns) x NRB warps on top of each other (rows).  Compile-time knobs so that
+// other shapes can be measured (-DS2G_G2D_NCG=2 -DS2G_G2D_NRB=5 -DS2G_G2D_CTAS=2: 320 threads, 96 registers).
+#ifndef S2G_G2D_NCG
+#define S2G_G2D_NCG 4
+#endif
+#ifndef S2G_G2D_NRB
+#define S2G_G2D_NRB 2
+#endif
+#ifndef S2G_G2D_CTAS
+#define S2G_G2D_CTAS 3
+#endif
+constexpr int NCG = S2G_G2D_NCG, NRB = S2G_G2D_NRB, G2D_CTAS = S2G_G2D_CTAS;
+constexpr int G2D_THREADS = 32 * NCG * NRB;
+constexpr int RPT = 8;                 // rows per thread
+constexpr int TILE_W = 16 * NCG;       // tile width  (j, the contiguous image axis)
+constexpr int TILE_H = 2 * RPT * NRB;  // tile height (i)
 constexpr int BATCH = 256;     // particle records staged in shared memory at a time
 constexpr int CHUNK = 4096;    // max pairs per work item
 
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(256) k_tile_chunks(const unsigned* __restrict_
 // accumulators after every batch of 256 records: per-pixel relative error ~1e-7 median, 1e-6 worst (bar of the mode:
 // 1e-5).  Records flagged !f32_ok (most of the kernel clipped away by the image border) take the FP64 chain.
 template <int KID, bool F32>
-__global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
+__global__ void __launch_bounds__(G2D_THREADS, G2D_CTAS) k_gather2d(const GRec* __restrict__ recs, const unsigned* __restrict__ vals,
                                                      const unsigned* __restrict__ tile_beg,
                                                      const unsigned* __restrict__ tile_end,
                                                      const unsigned* __restrict__ chunk_begin,  // ntiles+1
@@ -343,9 +357,9 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
     __shared__ unsigned s_work[3];
 
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-    const int jl = (wq & 3) * 16 + (lane & 15);   // column inside the tile
+    const int jl = (wq % NCG) * 16 + (lane & 15);  // column inside the tile
     const int rpar = lane >> 4;                   // row parity inside the warp
-    const int rblk = (wq >> 2) * (2 * RPT);       // first row of the warp's row block
+    const int rblk = (wq / NCG) * (2 * RPT);      // first row of the warp's row block
     unsigned touched = 0;
 
     for (;;) {
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
         if (tile == 0xffffffffu) break;
         const int i0 = (int)(tile / ntile_j) * TILE_H, j0 = (int)(tile % ntile_j) * TILE_W;
         const int j = j0 + jl;
-        const int jw0 = j0 + (wq & 3) * 16;   // first column of this warp (uniform)
+        const int jw0 = j0 + (wq % NCG) * 16;  // first column of this warp (uniform)
         const int wbase = i0 + rblk;          // first row of this warp (uniform)
         const int ibase = wbase + rpar;       // first row of this thread; its rows are ibase + 2r
         // this thread's column / first row centre inside the tile.  Opaque to the compiler on purpose: as plain functions
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
         for (unsigned b = wb; b < we; b += BATCH) {
             const int nb = (int)min((unsigned)BATCH, we - b);
             __syncthreads();  // previous batch fully consumed
-            if (tid < nb) {
+            for (int t = tid; t < nb; t += G2D_THREADS) {
                 // the shared-memory copy is made TILE-RELATIVE by the loading thread: x := x - i0, y := y - j0 (exact: a
                 // multiple of ulp(x) that is smaller than x, or a difference of at most h).  The per-(record, thread)
                 // offset is then ONE subtraction of the thread's constant (row + 0.5), a single rounding of the exact
@@ -415,14 +429,14 @@ __global__ void __launch_bounds__(256, 3) k_gather2d(const GRec* __restrict__ re
                 // (Scaling by 1/h BEFORE subtracting the thread's offset saves another instruction but cancels: the
                 // error grows to 64/h ulp, which the kernel rim (1-u)^k amplifies beyond the 1e-10 bar — measured.)
                 //   h := 2/h (row stride of a thread: its rows are two apart);  s_q := area_norm * quantity
-                GRec g = recs[vals[b + tid]];
+                GRec g = recs[vals[b + t]];
                 if (!F32) g.an *= shape_scale<KID>();  // exact (power of two), see shape_t_scaled
                 g.x = g.x - (double)i0;
                 g.y = g.y - (double)j0;
                 g.h = g.hinv + g.hinv;
-                s_rec[tid] = g;
-                s_q[tid] = g.an * ld_in(binq, (long long)n_images * g.p + image_k, in_dtype);
-                if constexpr (F32) s_f[tid] = make_float4((float)g.h, (float)g.dx_lo, (float)g.dx_hi, 0.0f);
+                s_rec[t] = g;
+                s_q[t] = g.an * ld_in(binq, (long long)n_images * g.p + image_k, in_dtype);
+                if constexpr (F32) s_f[t] = make_float4((float)g.h, (float)g.dx_lo, (float)g.dx_hi, 0.0f);
             }
             __syncthreads();
             for (int e = 0; e < nb; ++e) {
@@ -605,14 +619,14 @@ int launch_gather(s2g_ctx* ctx, const GRec* recs, const unsigned* vals, const un
                   const s2g_particles& P, const s2g_geom& G, int image_k, double* image)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * 3);
+    const int blocks = (int)std::min<long long>((long long)total_chunks, (long long)ctx->sm_count * G2D_CTAS);
     if (ctx->accum_f32)
-        k_gather2d<KID, true><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles,
+        k_gather2d<KID, true><<<max(blocks, 1), G2D_THREADS, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin, ntiles,
                                                                       ntile_j, total_chunks, P.binq, P.in_dtype,
                                                                       G.n_images, image_k, G.npix, image,
                                                                       ctx->d_counters);
     else
-        k_gather2d<KID, false><<<max(blocks, 1), 256, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin,
+        k_gather2d<KID, false><<<max(blocks, 1), G2D_THREADS, 0, ctx->stream>>>(recs, vals, tile_beg, tile_end, chunk_begin,
                                                                        ntiles, ntile_j, total_chunks, P.binq, P.in_dtype,
                                                                        G.n_images, image_k, G.npix, image,
                                                                        ctx->d_counters);
