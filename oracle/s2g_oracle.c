@@ -24,6 +24,9 @@
  *          healpix_base.cc algorithms, which Healpix.jl ports)
  *     For those two the status is "parity unpinned" (the only reference tests
  *     that would pin them need snapshots that are downloaded at test time).
+ *     ang2pix_ring / pix2ang_ring / pix2vec_ring are additionally checked against
+ *     the known answers printed in healpy's docstrings (Nside 16), i.e. against
+ *     the standard HEALPix library (tests/test_oracle_healpix.py).
  *   - CIC/TSC stencils: the reference holds no live code (tsc_interpolation.jl
  *     is fully commented out) -> semantics defined here, "parity unpinned".
  *

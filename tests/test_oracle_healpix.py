@@ -137,3 +137,30 @@ def test_healpix_map_filter_sort_quirks(oracle):
     q[3] = 0.0
     with pytest.raises(IndexError):
         oracle.healpix_map(p0.copy(), hsml, m, rho, q, w, center=center, nside=16, calc_mean=False)
+
+
+def test_published_healpy_known_answers(oracle):
+    """Known answers of the reference HEALPix implementation (healpy / HEALPix C++), as printed in healpy's own
+    docstrings for ang2pix, pix2ang, pix2vec and vec2pix at Nside 16 (RING scheme; quoted from the documentation — no
+    HEALPix library exists in this image).  Healpix.jl is validated against the same library, so these pin the oracle's
+    RING arithmetic to the standard at these vectors; everything else about Healpix.jl stays unpinned."""
+    L = oracle.lib()
+    th = [math.pi / 2, math.pi / 4, math.pi / 2, 0.0, math.pi]
+    ph = [0.0, math.pi / 4, math.pi / 2, 0.0, 0.0]
+    assert [L.s2go_hp_ang2pix_ring(16, a, b) for a, b in zip(th, ph)] == [1440, 427, 1520, 0, 3068]
+    t = C.c_double(); p = C.c_double()
+    L.s2go_hp_pix2ang_ring(16, 1440, C.byref(t), C.byref(p))
+    assert t.value == pytest.approx(1.5291175943723188, abs=1e-15) and p.value == 0.0
+    want_t = [1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608]
+    want_p = [0.0, 0.78539816, 1.61988371, 0.78539816, 0.78539816]
+    for pix, wt, wp in zip([1440, 427, 1520, 0, 3068], want_t, want_p):
+        L.s2go_hp_pix2ang_ring(16, pix, C.byref(t), C.byref(p))
+        assert t.value == pytest.approx(wt, abs=5e-9) and p.value == pytest.approx(wp, abs=5e-9)
+    v = np.zeros(3)
+    vp = v.ctypes.data_as(C.POINTER(C.c_double))
+    L.s2go_hp_pix2vec_ring(16, 1504, vp)
+    assert v == pytest.approx([0.99879545620517241, 0.049067674327418015, 0.0], abs=1e-15)
+    L.s2go_hp_pix2vec_ring(16, 1440, vp)
+    assert v == pytest.approx([0.99913157, 0.0, 0.04166667], abs=5e-9)
+    L.s2go_hp_pix2vec_ring(16, 427, vp)
+    assert v == pytest.approx([0.5000534, 0.5000534, 0.70703125], abs=5e-9)
