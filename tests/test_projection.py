@@ -55,6 +55,24 @@ def test_euler_rotation_host_vs_oracle(oracle):
     y = x.copy(); s2g.rotate_3D_(y, 10, 20, 30); assert np.array_equal(y, x)    # `rotate_3D!` does not mutate
 
 
+def test_reference_rotate_particles_testset():
+    """The reference's own "Rotate particles" testset (test/runtests.jl:101-137), literally: positions are Julia's
+    Matrix(3, N) there, (N, 3) rows here."""
+    import __graft_entry__ as ge
+    s2g = ge.load_package()
+    x_rand = np.random.default_rng(3).random((10, 3))
+    x_out = s2g.rotate_3D(x_rand, 0.0, 0.0, 0.0)                   # matrix, no rotation (:104-106)
+    assert np.allclose(x_out, x_rand, rtol=1.5e-8, atol=0)
+    s2g.rotate_3D_(x_out, 0.0, 0.0, 0.0)                           # "inplace" (:109-110)
+    assert np.allclose(x_out, x_rand, rtol=1.5e-8, atol=0)
+    x_in = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0]])            # two particles (1,1,0) (:113-115)
+    assert np.array_equal(s2g.project_along_axis(x_in.copy(), 3), x_in)                      # along z (:118-120)
+    assert np.array_equal(s2g.project_along_axis(x_in.copy(), 2), [[1.0, 0.0, 1.0]] * 2)     # along y (:123-130)
+    # the reference's "along x-axis" case calls axis 2 again (:133-136): same expectation
+    assert np.array_equal(s2g.project_along_axis(x_in.copy(), 2), [[1.0, 0.0, 1.0]] * 2)
+    assert np.array_equal(s2g.project_along_axis(x_in.copy(), 1), [[1.0, 0.0, 1.0]] * 2)     # yz: (y, z, x)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("projection", ["xy", "xz", "yz", (20.0, -35.0, 60.0)])
