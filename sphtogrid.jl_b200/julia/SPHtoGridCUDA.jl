@@ -358,4 +358,90 @@ function healpix_map_parallel!(allsky_map, weight_map, Pos::Matrix{Float64}, Hsm
     return allsky_map, weight_map
 end
 
+# ---------------------------------------------------------------------------------------------------------------
+# context knobs, housekeeping
+# ---------------------------------------------------------------------------------------------------------------
+version() = unsafe_string(ccall((:s2g_version, LIB), Cstring, ()))
+device_count() = Int(ccall((:s2g_device_count, LIB), Cint, ()))
+sync(ctx::Context=default_context()) = check(ccall((:s2g_sync, LIB), Cint, (Ptr{Cvoid},), ctx.handle))
+
+"strategy: :auto (per-particle choice by footprint size), :scatter (warp per particle, red.add), :gather (tile-owning CTAs)"
+set_strategy!(s::Symbol; ctx::Context=default_context()) =
+    check(ccall((:s2g_set_strategy, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle,
+                Dict(:auto => 0, :scatter => 1, :gather => 2)[s]))
+
+"force the numerical pass-A sum for every particle (default: closed form for unclipped, well resolved footprints)"
+set_exact_norm!(on::Bool; ctx::Context=default_context()) =
+    check(ccall((:s2g_set_exact_norm, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle, on))
+
+"accumulate mode: :f64 (default, 1e-10 against the CPU path) or :f32 (optional, 1e-5; 2D tile-gather kernel only)"
+set_accumulate_mode!(m::Symbol; ctx::Context=default_context()) =
+    check(ccall((:s2g_set_accumulate_mode, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle, Dict(:f64 => 0, :f32 => 1)[m]))
+
+"""
+    domain_decomposition(N, N_workers)
+
+src/parallel/domain_decomp.jl:7-17 through the library (needs no device): vector of 1-based `UnitRange`s.
+"""
+function domain_decomposition(N::Integer, N_workers::Integer)
+    starts = Vector{Int64}(undef, N_workers); counts = Vector{Int64}(undef, N_workers)
+    check(ccall((:s2g_domain_decomposition, LIB), Cint, (Int64, Int32, Ptr{Int64}, Ptr{Int64}), N, N_workers, starts,
+                counts))
+    return [(starts[i] + 1):(starts[i] + counts[i]) for i in 1:N_workers]
+end
+
+"""
+    center_and_filter!(Pos, par, par_centred)
+
+`center_particles` (src/cic_interpolation/filter_shift.jl:6-32: in place, in the precision of `Pos`, periodic wrap by
+`boxsize/2`) followed by `filter_particles_in_image` (:40-58) on the device; returns the `BitVector`-like mask.
+"""
+function center_and_filter!(Pos::Matrix{T}, par, par_centred; ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
+    N = size(Pos, 2)
+    mask = Vector{UInt8}(undef, N)
+    pos_out = similar(Pos)
+    shift = Float64.(par.center); zero3 = zeros(3); hs = Float64.(par_centred.halfsize)
+    GC.@preserve Pos pos_out mask shift zero3 hs begin
+        check(ccall((:s2g_center_filter, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Cvoid}, Ptr{UInt8}),
+                    ctx.handle, Pos, N, T == Float32 ? S2G_F32 : S2G_F64, shift, par.periodic, Float64(par.boxsize),
+                    zero3, hs, pos_out, mask))
+    end
+    Pos .= pos_out
+    return mask .!= 0x00
+end
+
+"""
+    cic_deposit(Pos, Bin_Q; param, dimensions=3, average=true, periodic=false)
+    tsc_deposit(Pos, Bin_Q; param, dimensions=3, average=true, periodic=false)
+
+Cloud-in-cell / triangular-shaped-cloud grid assignment (the reference's src/tsc_interpolation/tsc_interpolation.jl is
+commented out; semantics in DESIGN.md §6).  `Pos` relative to the image centre.  Returns the `(field, weight)` planes
+as `Matrix{Float64}(N^dims, 2)`, or the averaged grid when `average`.
+"""
+function _stencil(order::Integer, Pos::Matrix{T}, Bin_Q::Vector{T}; param, dimensions::Int=3, average::Bool=true,
+                  periodic::Bool=false, ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
+    n = param.Npixels[1]
+    image = Matrix{Float64}(undef, n^dimensions, 2)
+    GC.@preserve Pos Bin_Q image begin
+        check(ccall((:s2g_stencil_deposit, LIB), Cint,
+                    (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Float64, Int64, Int32,
+                     Ptr{Float64}, Ptr{Cvoid}),
+                    ctx.handle, order, dimensions, Pos, Bin_Q, length(Bin_Q), T == Float32 ? S2G_F32 : S2G_F64,
+                    Float64(param.len2pix), n, periodic, image, C_NULL))
+    end
+    average || return image
+    field = @views image[:, 1]; wgt = @views image[:, 2]
+    out = [wgt[i] > 0 ? field[i] / wgt[i] : field[i] for i in eachindex(field)]
+    return reshape(out, ntuple(_ -> n, dimensions))
+end
+cic_deposit(Pos, Bin_Q; kw...) = _stencil(2, Pos, Bin_Q; kw...)
+tsc_deposit(Pos, Bin_Q; kw...) = _stencil(3, Pos, Bin_Q; kw...)
+
+# The *_dev entry points (s2g_deposit_2d_dev, s2g_sphmap_dev, s2g_healpix_map_dev, s2g_reduce_image_*_dev,
+# s2g_stencil_deposit_dev, s2g_accumulate_finite_dev) take DEVICE pointers: they are for callers that already hold
+# their particles in GPU memory (CUDA.jl `CuArray`s: pass `pointer(x)`), with s2g_set_stream to order them after the
+# caller's own kernels.  They mirror the host-buffer calls above argument for argument (include/sphtogrid_cuda.h).
+
 end # module
