@@ -244,3 +244,85 @@ def hp_brute_disc(nside, theta, phi, radius):
         if math.acos(max(-1.0, min(1.0, float(v @ c)))) < radius:
             out.append(pix)
     return out
+
+
+def hp_pix2vec(nside, pix):
+    z, ph, _ = hp_pix_center(nside, pix)
+    s = math.sqrt(max(0.0, (1.0 - z) * (1.0 + z)))
+    return (s * math.cos(ph), s * math.sin(ph), z)
+
+
+def hp_ang2pix_brute(nside, theta, phi):
+    """pixel containing the direction, found as the nearest pixel centre among the pixels of the ring(s) around it —
+    independent of ang2pix_ring's index arithmetic.  (HEALPix pixels are not Voronoi cells of their centres; the test
+    that uses this mirror keeps the particle directions well inside a pixel, where the two agree.)"""
+    v = (math.sin(theta) * math.cos(phi), math.sin(theta) * math.sin(phi), math.cos(theta))
+    best, bd = -1, -2.0
+    for pix in range(12 * nside * nside):
+        c = hp_pix2vec(nside, pix)
+        d = v[0] * c[0] + v[1] * c[1] + v[2] * c[2]
+        if d > bd:
+            best, bd = pix, d
+    return best
+
+
+def healpix_deposit(pos, hsml, m, rho, binq, w, nside, kernel, kdim=2, calc_mean=True, centre_pixels=None):
+    """Second, independent restatement of the particle loop of healpix_map (src/healpix_interpolation/main.jl:143-213)
+    with calculate_weights / weight_per_index / contributing_area / distance_to_pixel_center
+    (pixel_weights.jl:6-140), contributing_pixels (constributing_pixels.jl:7-22: brute-force disc here),
+    particle_area_and_depth (main.jl:56-63) and update_image! (main.jl:25-45).  Pure Python loops: small Nside only.
+    `centre_pixels[p]` may supply ang2pix of particle p (otherwise the nearest pixel centre is used)."""
+    npix = 12 * nside * nside
+    amap = np.zeros(npix); wmap = np.zeros(npix)
+    ang_pix = math.sqrt(4.0 * PI / npix)
+    for p in range(len(hsml)):
+        if not calc_mean and binq[p] == 0:
+            continue
+        x = [float(pos[p, 0]), float(pos[p, 1]), float(pos[p, 2])]
+        dX = math.sqrt(x[0] ** 2 + x[1] ** 2 + x[2] ** 2)
+        if dX < hsml[p]:
+            continue
+        proj = math.asin(hsml[p] / dX)
+        theta = math.acos(x[2] / dX)
+        phi = math.atan2(x[1], x[0])
+        if phi < 0:
+            phi += 2 * PI
+        pix = hp_brute_disc(nside, theta, phi, proj)
+        cpix = centre_pixels[p] if centre_pixels is not None else hp_ang2pix_brute(nside, theta, phi)
+        if cpix not in pix:
+            pix.append(cpix)
+        dz = 2.0 * hsml[p]
+        area = (m[p] / rho[p]) / dz
+        dz /= (ang_pix * dX) ** 2
+        hinv = 1.0 / proj
+        A = []; wk = []
+        n_tot = n_distr = 0
+        d_area = d_w = 0.0
+        for q in pix:
+            c = hp_pix2vec(nside, q)
+            dot = x[0] * c[0] + x[1] * c[1] + x[2] * c[2]
+            dx = math.acos(min(dot / dX, 1.0))
+            u = dx * hinv
+            a = max(0.0, min(ang_pix, abs(proj - (dx - 0.5 * ang_pix)))) / ang_pix
+            a /= (ang_pix * dX) ** 2
+            d_area += a
+            n_tot += 1
+            if u <= 1:
+                k = W(kernel, kdim, u, hinv)
+                d_w += k * a
+                n_distr += 1
+            else:
+                k = 0.0
+            A.append(a); wk.append(k)
+        if d_w == 0.0:
+            n_distr = n_tot
+            wk = [1.0] * len(pix)
+            wpp = n_distr / d_area if d_area != 0 else 1.0
+        else:
+            wpp = n_distr / d_w
+        an = (area / n_distr) * wpp * w[p] * dz
+        for q, a, k in zip(pix, A, wk):
+            pw = an * k * a
+            amap[q] += binq[p] * pw
+            wmap[q] += pw
+    return amap, wmap
