@@ -27,24 +27,47 @@ KERNEL_IDS = {"Cubic": 0, "Quintic": 1, "WendlandC2": 2, "WendlandC4": 3, "Wendl
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "s2g_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("s2g_oracle.c", "s2g_oracle_exact.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _LIB_PATH
 
 
-_lib = None
+_libs = {}
+_which = "checker"
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int64)
 _bp = C.POINTER(C.c_uint8)
 
 
+def select_library(which="checker", native=True):
+    """"checker" (default): libs2g_oracle.so, -O2 -ffp-contract=off — the ONLY build parity is judged with.
+    "fast": libs2g_oracle_fast.so, -O3 with FMA contraction — the CPU-baseline timing leg of bench.py; with
+    `native` it is first rebuilt with -march=native for the host it runs on (falls back to the shipped x86-64-v3
+    build when there is no compiler)."""
+    global _which
+    if which not in ("checker", "fast"):
+        raise ValueError(which)
+    if which == "fast" and "fast" not in _libs and native:
+        try:
+            subprocess.run(["make", "-C", _HERE, "fast", "FAST_ARCH=-march=native"], check=True, capture_output=True)
+        except Exception:
+            pass
+    _which = which
+    return lib()
+
+
 def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+    if _which not in _libs:
+        if _which == "checker":
+            build()
+            path = _LIB_PATH
+        else:
+            path = os.path.join(_HERE, "libs2g_oracle_fast.so")
+            if not os.path.exists(path):
+                subprocess.run(["make", "-C", _HERE, "fast"], check=True, capture_output=True)
+        L = C.CDLL(path)
         L.s2go_kernel_shape.restype = C.c_double
         L.s2go_kernel_shape.argtypes = [C.c_int, C.c_double]
         L.s2go_kernel_value.restype = C.c_double
@@ -72,7 +95,7 @@ def lib():
                                                       _dp, _ip, _ip, _dp]
         L.s2go_cic_mapping_parallel.restype = C.c_int
         L.s2go_cic_mapping_parallel.argtypes = [C.c_int] + [_dp] * 6 + [C.c_int64, C.c_int, C.c_double, C.c_int64,
-                                                                       C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+                                                                       C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip]
         L.s2go_max_threads.restype = C.c_int
         L.s2go_reduce_image_2d.argtypes = [_dp, C.c_int64, C.c_int64, C.c_int, C.c_int, _dp]
         L.s2go_reduce_image_3d.argtypes = [_dp, C.c_int64, C.c_int, _dp]
@@ -93,8 +116,14 @@ def lib():
                                                                 C.c_int, _dp, _dp]
         L.s2go_stencil_deposit.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int64, C.c_double, C.c_int64, C.c_int, _dp]
         L.s2go_stencil_average.argtypes = [_dp, C.c_int64, _dp]
-        _lib = L
-    return _lib
+        L.s2go_healpix_deposit_exact.restype = C.c_int
+        L.s2go_healpix_deposit_exact.argtypes = [_dp] * 6 + [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                                             _ip, _dp]
+        L.s2go_healpix_deposit_chord64.restype = C.c_int
+        L.s2go_healpix_deposit_chord64.argtypes = [_dp] * 6 + [C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _dp]
+        L.s2go_hp_angdist_exact.argtypes = [C.c_int64, C.c_int64, _dp, _dp, C.c_void_p]
+        _libs[_which] = L
+    return _libs[_which]
 
 
 def _d(a):
@@ -209,7 +238,7 @@ def cic_mapping_2d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel="WendlandC6
     if n_workers and n_workers > 0:
         rc = lib().s2go_cic_mapping_parallel(2, _d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, n_images,
                                              float(len2pix), int(npix), kid, kernel_dim, int(calc_mean),
-                                             int(n_workers), _d(image))
+                                             int(n_workers), _d(image), _i(st))
     else:
         rc = lib().s2go_cic_mapping_2d(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, n_images,
                                        float(len2pix), int(npix), kid, kernel_dim, int(calc_mean), _d(image), _i(fp),
@@ -251,7 +280,7 @@ def cic_mapping_3d(pos, hsml, m, rho, binq, w, len2pix, npix, kernel="Cubic", ke
     if n_workers and n_workers > 0:
         rc = lib().s2go_cic_mapping_parallel(3, _d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, 1,
                                              float(len2pix), int(npix), kid, kernel_dim, int(calc_mean),
-                                             int(n_workers), _d(image))
+                                             int(n_workers), _d(image), _i(st))
     else:
         rc = lib().s2go_cic_mapping_3d(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, float(len2pix),
                                        int(npix), kid, kernel_dim, int(calc_mean), _d(image), _i(fp), _i(st),
@@ -387,14 +416,28 @@ def map_it(pos_in, hsml, m, rho, binq, weights, *, param: MappingParameters, ker
 
 
 # --------------------------------------------------------------------------- HEALPix
-def healpix_deposit(pos, hsml, m, rho, binq, w, nside, kernel="WendlandC4", kernel_dim=2, calc_mean=True, n_workers=0):
+def healpix_deposit(pos, hsml, m, rho, binq, w, nside, kernel="WendlandC4", kernel_dim=2, calc_mean=True, n_workers=0,
+                    exact=False):
+    """main.jl:143-213.  `exact=True`: the extended-precision arbiter (s2g_oracle_exact.c) — same pixel lists, weights
+    in long double; `n_workers` threads share the maps through atomics there.  `exact="sens"` additionally returns
+    stats["sens"] / stats["sens_q"], the per-pixel sensitivities Σ|∂pix_weight/∂dx| of the weight map and Σ|q ∂pix_weight/∂dx|
+    of the quantity map (see s2go_healpix_deposit_exact)."""
     pos = _c64(pos); hsml = _c64(hsml); m = _c64(m); rho = _c64(rho); w = _c64(w); binq = _c64(binq)
     n = hsml.shape[0]
     npix = 12 * nside * nside
     amap = np.zeros(npix); wmap = np.zeros(npix)
     st = np.zeros(4, dtype=np.int64)
     kid = KERNEL_IDS[kernel]
-    if n_workers and n_workers > 0:
+    if exact:
+        sens = np.zeros(2 * npix) if exact == "sens" else None
+        lib().s2go_healpix_deposit_exact(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, nside, kid,
+                                         int(calc_mean), int(n_workers or 1), _d(amap), _d(wmap), _i(st),
+                                         _d(sens) if sens is not None else None)
+        if sens is not None:
+            stats = dict(n_mapped=int(st[0]), footprint_pixels=int(st[1]), touched_pixels=int(st[2]),
+                         n_fallback=int(st[3]), sens=sens[:npix], sens_q=sens[npix:])
+            return amap, wmap, stats
+    elif n_workers and n_workers > 0:
         lib().s2go_healpix_deposit_parallel(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), n, nside, kid,
                                             kernel_dim, int(calc_mean), int(n_workers), _d(amap), _d(wmap))
     else:
@@ -421,15 +464,15 @@ def filter_sort_particles(pos, hsml, m, rho, binq, weights, center, radius_limit
 
 
 def healpix_map(pos, hsml, m, rho, binq, weights, *, center=(0.0, 0.0, 0.0), radius_limits=(0.0, np.inf), nside=1024,
-                kernel="WendlandC4", kernel_dim=2, calc_mean=True, n_workers=0):
+                kernel="WendlandC4", kernel_dim=2, calc_mean=True, n_workers=0, exact=False):
     """main.jl:92-227.  pos (N,3) f64, mutated in place (Q1).  Returns (map, weight_map), un-reduced."""
     pos = _pos3xn(pos)
     npix = 12 * nside * nside
     if (not calc_mean) and np.sum(binq) == 0:
         return np.zeros(npix), np.zeros(npix)
     p, h, mm, rr, bq, ww = filter_sort_particles(pos, hsml, m, rho, binq, weights, center, radius_limits, calc_mean)
-    a, wm, _ = healpix_deposit(p, h, mm, rr, bq, ww, nside, kernel, kernel_dim, calc_mean, n_workers)
-    return a, wm
+    a, wm, st = healpix_deposit(p, h, mm, rr, bq, ww, nside, kernel, kernel_dim, calc_mean, n_workers, exact)
+    return (a, wm, st) if exact == "sens" else (a, wm)
 
 
 # --------------------------------------------------------------------------- stencils
@@ -454,3 +497,22 @@ def kernel_shape(kernel, u):
 
 def kernel_value(kernel, dim, u, h_inv):
     return lib().s2go_kernel_value(KERNEL_IDS[kernel], dim, float(u), float(h_inv))
+
+
+def hp_angdist_exact(nside, pix, pos):
+    """(long-double chord form, __float128 literal acos(min(d/r,1)), long-double acos form) of the angle between the
+    particle at `pos` and the centre of RING pixel `pix`; plus the raw long doubles (np.longdouble[3])."""
+    out = np.zeros(3)
+    raw = np.zeros(3, dtype=np.longdouble)
+    lib().s2go_hp_angdist_exact(int(nside), int(pix), _d(_c64(pos)), _d(out), raw.ctypes.data)
+    return out, raw
+
+
+def healpix_deposit_chord64(pos, hsml, m, rho, binq, w, nside, kernel="WendlandC4", calc_mean=True):
+    """Float64 chord formulation (what the CUDA kernels evaluate), on the CPU — conditioning study only."""
+    pos = _c64(pos); hsml = _c64(hsml); m = _c64(m); rho = _c64(rho); w = _c64(w); binq = _c64(binq)
+    npix = 12 * nside * nside
+    amap = np.zeros(npix); wmap = np.zeros(npix)
+    lib().s2go_healpix_deposit_chord64(_d(pos), _d(hsml), _d(m), _d(rho), _d(binq), _d(w), hsml.shape[0], nside,
+                                       KERNEL_IDS[kernel], int(calc_mean), _d(amap), _d(wmap))
+    return amap, wmap

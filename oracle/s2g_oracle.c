@@ -566,9 +566,10 @@ S2GO_API int s2go_cic_mapping_3d(const double* pos, const double* hsml, const do
 S2GO_API int s2go_cic_mapping_parallel(int dims, const double* pos, const double* hsml, const double* m,
                                        const double* rho, const double* binq, const double* w, int64_t n, int n_images,
                                        double len2pix, int64_t npix, int kid, int kdim, int calc_mean, int n_workers,
-                                       double* image)
+                                       double* image, int64_t* stats4 /* may be NULL: counters summed over the slices */)
 {
     if (n_workers < 1) n_workers = 1;
+    s2go_stats* wst = (s2go_stats*)calloc((size_t)n_workers * 8, sizeof(s2go_stats)); /* stride 8: one cache line pair per worker */
     const int64_t N_distr = dims == 2 ? npix * npix : npix * npix * npix;
     const int planes = dims == 2 ? n_images + 1 : 2;
     int64_t* start = (int64_t*)malloc(sizeof(int64_t) * (size_t)n_workers);
@@ -585,10 +586,10 @@ S2GO_API int s2go_cic_mapping_parallel(int dims, const double* pos, const double
             fail = 1;
         } else if (dims == 2)
             cic_mapping_2d_range(pos, hsml, m, rho, binq, w, start[t], end[t], n_images, len2pix, npix, kid, kdim,
-                                 calc_mean, img, wk, A, NULL, NULL, NULL, 0, NULL);
+                                 calc_mean, img, wk, A, NULL, &wst[8 * t], NULL, 0, NULL);
         else
             cic_mapping_3d_range(pos, hsml, m, rho, binq, w, start[t], end[t], len2pix, npix, kid, kdim, calc_mean, img,
-                                 wk, A, NULL, NULL, NULL);
+                                 wk, A, NULL, &wst[8 * t], NULL);
         free(wk); free(A);
         partial[t] = img;
     }
@@ -601,8 +602,15 @@ S2GO_API int s2go_cic_mapping_parallel(int dims, const double* pos, const double
             image[e] = s;
         }
     }
+    if (stats4) {
+        stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0;
+        for (int t = 0; t < n_workers; t++) {
+            stats4[0] += wst[8 * t].n_mapped; stats4[1] += wst[8 * t].footprint_pixels;
+            stats4[2] += wst[8 * t].touched_pixels; stats4[3] += wst[8 * t].n_fallback;
+        }
+    }
     for (int t = 0; t < n_workers; t++) free(partial[t]);
-    free(partial); free(start); free(end);
+    free(partial); free(start); free(end); free(wst);
     return fail ? -1 : 0;
 }
 

@@ -110,22 +110,27 @@ __device__ __forceinline__ RingTrig hp_ring_trig(const HpGeom& g, long long ring
 {
     RingTrig t;
     double z, den;
+    // pix2vecRing = (sinθ cosφ, sinθ sinφ, cosθ) with θ = acos(z): cosθ = z and sinθ = sqrt((1-z)(1+z)) without the
+    // round trip through acos.  In the polar caps 1-|z| = ring²/(3 Nside²) is taken directly (no cancellation: next
+    // to a pole 1-z ~ 1e-7 and 1 - (1 - x) would keep only 9 digits of sinθ); DESIGN.md "HEALPix conditioning".
     if (ring < g.nside) {
-        z = __dadd_rn(1.0, -__ddiv_rn((double)(ring * ring), g.fact2_p2a));
+        const double omz = __ddiv_rn((double)(ring * ring), g.fact2_p2a);
+        z = 1.0 - omz;
+        t.st = sqrt(omz * (2.0 - omz));
         t.off = 0.5; den = __dmul_rn(2.0, (double)ring);
     } else if (ring <= 3 * g.nside) {
         z = __ddiv_rn((double)(g.nl2 - ring), g.fact1_p2a);
+        t.st = sqrt((1.0 - z) * (1.0 + z));
         t.off = 0.5 * (double)(1 + ((ring + g.nside) & 1));
         den = __dmul_rn(2.0, (double)g.nside);
     } else {
         const long long rs = g.nl4 - ring;
-        z = __dadd_rn(-1.0, __ddiv_rn((double)(rs * rs), g.fact2_p2a));
+        const double opz = __ddiv_rn((double)(rs * rs), g.fact2_p2a);
+        z = opz - 1.0;
+        t.st = sqrt(opz * (2.0 - opz));
         t.off = 0.5; den = __dmul_rn(2.0, (double)rs);
     }
-    // pix2vecRing = (sinθ cosφ, sinθ sinφ, cosθ) with θ = acos(z): cosθ = z and sinθ = sqrt((1-z)(1+z)) without the
-    // round trip through acos (differs from sin(acos(z)) by a few ulp; see DESIGN.md "HEALPix conditioning")
     t.ct = z;
-    t.st = sqrt((1.0 - z) * (1.0 + z));
     t.inv_den = 1.0 / den;
     return t;
 }

@@ -62,9 +62,25 @@ def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid
     """Body of sphMapping(parallel=true) on this rank's GPU.  Every rank holds the full input (like the reference's
     master) and deposits its own contiguous slice; every rank returns the full result."""
     import torch
+    from .mapping import center_particles
     ws, rank = world()
     n = pos.shape[0]
     s, e = shard_range(n, ws, rank)
+    want = np.float32 if code == 0 else np.float64
+    for name, a in (("HSML", hs), ("M", mm), ("Rho", rr), ("Bin_Quant", bq), ("Weights", ww)):
+        if a.dtype != want:
+            raise TypeError(f"sph_mapping_sharded: {name} is {a.dtype}, the call was declared {np.dtype(want)} "
+                            "(sphMapping converts the fields before sharding)")
+    shift, periodic, boxsize = param.center, int(param.periodic), float(param.boxsize)
+    recentre_after = True
+    if pos.dtype != want:
+        # Float32 positions with Float64 fields (the common Gadget case): recentre in Float32 like the reference (Q2),
+        # then deposit the widened copy without a further shift — s2g_sphmap_dev reads ONE dtype for all arrays
+        center_particles(pos, param, ctx=ctx)
+        pos_up = np.ascontiguousarray(pos[s:e], dtype=want)
+        shift, periodic, boxsize, recentre_after = [0.0, 0.0, 0.0], 0, -1.0, False
+    else:
+        pos_up = pos[s:e]
     npix = int(par.Npixels[0])
     ncell = npix * npix if dimensions == 2 else npix ** 3
     planes = nim + 1 if dimensions == 2 else 2
@@ -72,11 +88,12 @@ def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid
     with torch.cuda.device(dev):
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a[s:e])).to(dev, non_blocking=False)
-        d_pos, d_hs, d_m, d_r, d_q, d_w = up(pos), up(hs), up(mm), up(rr), up(bq), up(ww)
+        d_pos = torch.from_numpy(np.ascontiguousarray(pos_up)).to(dev, non_blocking=False)
+        d_hs, d_m, d_r, d_q, d_w = up(hs), up(mm), up(rr), up(bq), up(ww)
         image = torch.zeros(ncell * planes, dtype=torch.float64, device=dev)
         check(lib().s2g_sphmap_dev(ctx.handle, dimensions, ptr(d_pos.data_ptr()), ptr(d_hs.data_ptr()),
                                    ptr(d_m.data_ptr()), ptr(d_r.data_ptr()), ptr(d_q.data_ptr()), ptr(d_w.data_ptr()),
-                                   e - s, nim, code, dbl3(param.center), int(param.periodic), float(param.boxsize),
+                                   e - s, nim, code, dbl3(shift), periodic, boxsize,
                                    dbl3(par.halfsize), float(par.len2pix), npix, kid, int(calc_mean), 0,
                                    ptr(image.data_ptr())))
         allreduce_sum_(image)  # image = sum(fetch.(futures))
@@ -94,8 +111,8 @@ def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid
                 out = red.cpu().numpy().reshape((npix, npix, npix), order="F")
         torch.cuda.current_stream(dev).synchronize()
     # Q1: the reference recentres the caller's Pos before slicing
-    from .mapping import center_particles
-    center_particles(pos, param, ctx=ctx)
+    if recentre_after:
+        center_particles(pos, param, ctx=ctx)
     return out
 
 

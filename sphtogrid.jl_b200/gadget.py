@@ -69,20 +69,45 @@ def _resolve(filename):
 
 
 def _scan_blocks(f):
-    """{name: (offset of payload, payload bytes)} by walking the label records"""
+    """{name: (offset of payload, payload bytes)} by walking the label records.  Record markers are UNSIGNED 32-bit:
+    a block of >= 4 GiB (POS in Float32 from ~358 M particles, in Float64 from ~179 M) wraps modulo 2^32, so the true
+    payload size is the smallest `marker + k*2^32` whose trailing marker matches and after which the file either ends
+    or continues with a well-formed label record (what GadgetIO does with the header's particle counts, without
+    needing the element type)."""
     out = {}
     f.seek(0, os.SEEK_END)
     size = f.tell()
     pos = 0
     while pos + 16 <= size:
         f.seek(pos)
-        lead, name, nxt, trail = struct.unpack("<i4sii", f.read(16))
+        lead, name, nxt, trail = struct.unpack("<I4sII", f.read(16))
         if lead != 8 or trail != 8:
             raise ValueError("not a Gadget format-2 snapshot (label record marker != 8; format 1 and big-endian files "
                              "are not supported)")
-        nbytes, = struct.unpack("<i", f.read(4))
+        marker, = struct.unpack("<I", f.read(4))
+        nbytes = None
+        cand = marker
+        while pos + 20 + cand + 4 <= size:
+            f.seek(pos + 20 + cand)
+            tail, = struct.unpack("<I", f.read(4))
+            end = pos + 24 + cand
+            ok = tail == marker
+            if ok and end + 16 <= size:
+                l2, _, _, t2 = struct.unpack("<I4sII", f.read(16))
+                ok = l2 == 8 and t2 == 8
+            elif ok:
+                ok = end == size
+            if ok:
+                nbytes = cand
+                break
+            cand += 1 << 32
+        if nbytes is None:
+            raise ValueError(f"block {name!r}: no payload size congruent to its record marker {marker} (mod 2^32) "
+                             "ends on a matching trailing marker")
+        if (nxt - 8) % (1 << 32) != marker:
+            raise ValueError(f"block {name!r}: label record and data record disagree on the payload size")
         out[name.decode("ascii").strip()] = (pos + 20, nbytes)
-        pos += 16 + nxt
+        pos += 24 + nbytes
     return out
 
 
@@ -168,10 +193,11 @@ def write_snapshot(filename, header: SnapshotHeader, blocks: dict, with_info=Fal
     """Writes a format-2 (sub-)file: `blocks` maps a block name to the payload array already concatenated over the
     particle types the block carries.  Used by the tests and for synthetic inputs."""
     def record(f, name, payload: bytes):
-        f.write(struct.pack("<i4sii", 8, f"{name:<4}".encode("ascii"), len(payload) + 8, 8))
-        f.write(struct.pack("<i", len(payload)))
+        m32 = 1 << 32   # record markers are unsigned 32-bit and wrap for blocks >= 4 GiB
+        f.write(struct.pack("<I4sII", 8, f"{name:<4}".encode("ascii"), (len(payload) + 8) % m32, 8))
+        f.write(struct.pack("<I", len(payload) % m32))
         f.write(payload)
-        f.write(struct.pack("<i", len(payload)))
+        f.write(struct.pack("<I", len(payload) % m32))
 
     with open(filename, "wb") as f:
         record(f, "HEAD", header.pack())

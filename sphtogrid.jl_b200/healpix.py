@@ -51,11 +51,32 @@ def healpix_deposit(pos, hsml, m, rho, bin_q, weights, Nside, kernel, calc_mean=
 
 def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), radius_limits=(0.0, np.inf),
                 Nside=1024, kernel, show_progress=True, output_from_all_workers=False, calc_mean=True, ctx=None,
-                group=None):
+                group=None, strict_reference=True):
     """Calculate an allsky map from SPH particles.  Returns `(image, weight_image)` in RING order (0-based storage =
     Julia pixels[i+1]); divide to reduce the image (main.jl:76-77).  `group=DeviceGroup(...)` spreads the particle loop
-    over the GPUs of the group (same result: the shell selection is made over all particles, s2g_group_healpix_map)."""
+    over the GPUs of the group (same result: the shell selection is made over all particles, s2g_group_healpix_map).
+
+    `strict_reference=True` (default) is bug-compatible with filter_sort_particles (filter_particles.jl:28-41): the
+    shell mask in ORIGINAL order indexes the far-to-near permutation (`sorted[sel]`), so as soon as one particle lies
+    outside the shell the `count(sel)` deposited particles are picked by radial rank, not by membership (a
+    `RuntimeWarning` says so), and `calc_mean=False` raises the reference's BoundsError unless every particle is in
+    the shell with `Bin_q > 0`.  `strict_reference=False` (no reference counterpart) maps exactly the particles
+    inside the shell (with `Bin_q > 0` when `calc_mean=False`), far to near."""
     npix = 12 * int(Nside) ** 2
+    if not strict_reference:
+        pos = _as_pos(Pos)
+        if pos.dtype != np.float64:
+            raise TypeError("healpix_map requires Float64 inputs (method signatures `where T`, pixel_weights.jl:87-91)")
+        pos -= np.asarray(center, dtype=np.float64)[None, :]
+        dx = np.sqrt(pos[:, 0] ** 2 + pos[:, 1] ** 2 + pos[:, 2] ** 2)
+        keep = find_in_shell(dx, radius_limits)
+        if not calc_mean:
+            keep &= np.asarray(Bin_q) > 0.0
+        idx = np.flatnonzero(keep)
+        idx = idx[np.argsort(dx[idx], kind="stable")[::-1]]
+        g = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64)[idx])
+        return healpix_deposit(np.ascontiguousarray(pos[idx]), g(Hsml), g(M), g(Rho), g(Bin_q), g(Weights), Nside,
+                               kernel, calc_mean, ctx=ctx or (group.context(0) if group is not None else None))
     if (not calc_mean) and np.sum(Bin_q) == 0:
         return np.zeros(npix), np.zeros(npix)
     pos = _as_pos(Pos)
@@ -78,6 +99,16 @@ def healpix_map(Pos, Hsml, M, Rho, Bin_q, Weights, *, center=(0.0, 0.0, 0.0), ra
                              f"[{n_short}-element BitVector]")
     amap = np.zeros(npix); wmap = np.zeros(npix)
     pos_out = np.empty_like(pos)
+    if np.isfinite(radius_limits[1]) or radius_limits[0] > 0.0:
+        dx_ = np.sqrt((pos[:, 0] - center[0]) ** 2 + (pos[:, 1] - center[1]) ** 2 + (pos[:, 2] - center[2]) ** 2)
+        n_out = n - int(np.count_nonzero(find_in_shell(dx_, radius_limits)))
+        if n_out:
+            import warnings
+            warnings.warn(f"healpix_map: {n_out} of {n} particles lie outside radius_limits; the reference indexes the "
+                          "far-to-near permutation with the unsorted shell mask (filter_particles.jl:33-41), so the "
+                          "deposited particles are chosen by radial rank, not by shell membership — reproduced here; "
+                          "pass strict_reference=False to map the particles inside the shell", RuntimeWarning,
+                          stacklevel=2)
     cen = (C.c_double * 3)(*[float(c) for c in center])
     rl = (C.c_double * 2)(float(radius_limits[0]), float(radius_limits[1]))
     if group is not None:

@@ -63,6 +63,37 @@ function _uniform(Pos, HSML, M, Rho, Bin_Q, Weights)
 end
 
 """
+    _uniform_fused!(Pos, HSML, M, Rho, Bin_Q, Weights, par, ctx) -> (T, pos, hsml, m, rho, bq, w, shift, periodic, boxsize, writeback)
+
+Element type rule of the fused calls: `Float32` only if EVERY array is `Float32`, otherwise everything is widened to
+`Float64` — never narrowed (the reference promotes: `bin_q = Float64(Bin_Q[p])`, cic_2D.jl:186-199; `get_quantities_2D`
+multiplies by the Float64 `len2pix`).  With Float32 positions and Float64 fields the positions are first recentred in
+Float32 (center_particles works in the precision of `Pos`, filter_shift.jl:15 — quirk Q2), written back into `Pos`,
+and the widened copy is then mapped with a zero shift.
+"""
+function _uniform_fused!(Pos::Matrix, HSML, M, Rho, Bin_Q, Weights, par, ctx)
+    T = (eltype(Pos) == Float32 && all(a -> eltype(a) == Float32, (HSML, M, Rho, Bin_Q, Weights))) ? Float32 : Float64
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    shift = Float64.(par.center); periodic = par.periodic; boxsize = Float64(par.boxsize)
+    if eltype(Pos) == T
+        return T, Pos, conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights), shift, periodic, boxsize, true
+    end
+    # mixed: recentre in the precision of Pos on the device (mask not needed), then widen
+    N = size(Pos, 2)
+    mask = Vector{UInt8}(undef, N); pos_c = similar(Pos); zero3 = zeros(3); big3 = fill(Inf, 3)
+    GC.@preserve Pos pos_c mask shift zero3 big3 begin
+        check(ccall((:s2g_center_filter, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Cvoid}, Ptr{UInt8}),
+                    ctx.handle, Pos, N, eltype(Pos) == Float32 ? S2G_F32 : S2G_F64, shift, periodic, boxsize,
+                    zero3, big3, pos_c, mask))
+    end
+    Pos .= pos_c
+    return T, convert(Matrix{T}, Pos), conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights), zeros(3), false,
+           -1.0, false
+end
+
+"""
     cic_mapping_2D(Pos, HSML, M, Rho, Bin_Q, Weights, RM=nothing; param, kernel, show_progress, calc_mean, stokes)
 
 Drop-in for src/cic_interpolation/cic_2D.jl:103-244.  Returns `Matrix{Float64}(Nx*Ny, N_images+1)`.
@@ -202,26 +233,27 @@ recentred in place exactly like center_particles does (src/cic_interpolation/fil
 function sphmap_fused(Pos::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions::Int=2,
                       calc_mean::Bool=false, reduce_image::Bool=true, return_both_maps::Bool=false,
                       ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
-    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
-    hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+    U, pos, hsml, m, rho, bq, w, shift, periodic, boxsize, writeback =
+        _uniform_fused!(Pos, HSML, M, Rho, Bin_Q, Weights, param, ctx)
     N = length(m)
     n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
     n = par_centred.Npixels[1]
     out = dimensions == 2 ? (return_both_maps ? Matrix{Float64}(undef, n * n, n_images + 1) :
                                                 Array{Float64,3}(undef, n, n, n_images)) :
                             Array{Float64,3}(undef, n, n, n)
-    shift = Float64.(param.center); half = Float64.(par_centred.halfsize)
-    pos_out = similar(Pos)
-    GC.@preserve Pos hsml m rho bq w out shift half pos_out begin
+    half = Float64.(par_centred.halfsize)
+    pos_out = writeback ? similar(pos) : pos
+    GC.@preserve pos hsml m rho bq w out shift half pos_out begin
         check(ccall((:s2g_sphmap, LIB), Cint,
                     (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
                      Int64, Int32, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Float64, Int64, Int32, Int32,
                      Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
-                    ctx.handle, dimensions, Pos, hsml, m, rho, bq, w, N, n_images, T == Float32 ? S2G_F32 : S2G_F64,
-                    shift, param.periodic, Float64(param.boxsize), half, Float64(par_centred.len2pix), n,
-                    kernel_id(kernel), calc_mean, reduce_image, return_both_maps, pos_out, out, C_NULL))
+                    ctx.handle, dimensions, pos, hsml, m, rho, bq, w, N, n_images, U == Float32 ? S2G_F32 : S2G_F64,
+                    shift, periodic, boxsize, half, Float64(par_centred.len2pix), n,
+                    kernel_id(kernel), calc_mean, reduce_image, return_both_maps,
+                    writeback ? pointer(pos_out) : C_NULL, out, C_NULL))
     end
-    Pos .= pos_out
+    writeback && (Pos .= pos_out)
     return out
 end
 
@@ -248,7 +280,19 @@ function sphmap_projected(pos_in::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; proje
         error("projection must be either along in 'xy', 'xz', or 'yz' plane of defined by a vector of Euler angles!")
     end
     _, par_centred = center_particles(Matrix{T}(undef, 3, 0), par)   # only the recentred parameters are needed
-    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
+    if !(T == Float32 && all(a -> eltype(a) == Float32, (HSML, M, Rho, Bin_Q, Weights))) && T != Float64
+        # Float32 positions with Float64 fields: never narrow the fields.  Rotate/permute + recentre a COPY in Float32
+        # like map_it does (cic_interpolation.jl:327-345, filter_shift.jl:15), then run the unprojected fused call.
+        pos = copy(pos_in)
+        if perm !== C_NULL
+            pos = pos[perm .+ 1, :]
+        elseif rot !== C_NULL
+            pos = Matrix{T}(reshape(rot, 3, 3)' * pos)
+        end
+        return sphmap_fused(pos, HSML, M, Rho, Bin_Q, Weights; param=par, par_centred=par_centred, kernel=kernel,
+                            dimensions=dimensions, calc_mean=calc_mean, reduce_image=reduce_image, ctx=ctx)
+    end
+    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)   # T == Float64 here unless every array is Float32: widening only
     hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
     N = length(m)
     n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
@@ -306,28 +350,29 @@ Body of `sphMapping(...; parallel=true)` (cic_interpolation.jl:171-215 for 2D, :
 """
 function sphmap_parallel(Pos::Matrix{T}, HSML, M, Rho, Bin_Q, Weights; param, par_centred, kernel, dimensions::Int=2,
                          calc_mean::Bool=false, reduce_image::Bool=true, return_both_maps::Bool=false,
-                         group::DeviceGroup=default_group()) where {T<:Union{Float32,Float64}}
-    conv(a) = eltype(a) == T ? a : convert(Array{T}, a)
-    hsml, m, rho, bq, w = conv(HSML), conv(M), conv(Rho), conv(Bin_Q), conv(Weights)
+                         group::DeviceGroup=default_group(),
+                         ctx::Context=default_context()) where {T<:Union{Float32,Float64}}
+    U, pos, hsml, m, rho, bq, w, shift, periodic, boxsize, writeback =
+        _uniform_fused!(Pos, HSML, M, Rho, Bin_Q, Weights, param, ctx)
     N = length(m)
     n_images = ndims(bq) == 1 ? 1 : size(bq, 1)
     n = par_centred.Npixels[1]
     out = dimensions == 2 ? (return_both_maps ? Matrix{Float64}(undef, n * n, n_images + 1) :
                                                 Array{Float64,3}(undef, n, n, n_images)) :
                             Array{Float64,3}(undef, n, n, n)
-    shift = Float64.(param.center); half = Float64.(par_centred.halfsize)
-    pos_out = similar(Pos)
-    GC.@preserve Pos hsml m rho bq w out shift half pos_out begin
+    half = Float64.(par_centred.halfsize)
+    pos_out = writeback ? similar(pos) : pos
+    GC.@preserve pos hsml m rho bq w out shift half pos_out begin
         check(ccall((:s2g_group_sphmap, LIB), Cint,
                     (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
                      Int64, Int32, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Float64, Int64, Int32, Int32,
                      Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
-                    group.handle, dimensions, Pos, hsml, m, rho, bq, w, N, n_images,
-                    T == Float32 ? S2G_F32 : S2G_F64, shift, param.periodic, Float64(param.boxsize), half,
+                    group.handle, dimensions, pos, hsml, m, rho, bq, w, N, n_images,
+                    U == Float32 ? S2G_F32 : S2G_F64, shift, periodic, boxsize, half,
                     Float64(par_centred.len2pix), n, kernel_id(kernel), calc_mean, reduce_image, return_both_maps,
-                    pos_out, out, C_NULL))
+                    writeback ? pointer(pos_out) : C_NULL, out, C_NULL))
     end
-    Pos .= pos_out
+    writeback && (Pos .= pos_out)
     return out
 end
 

@@ -350,8 +350,14 @@ def map_it(pos_in, hsml, mass, rho, bin_q, weights, RM=None, *, param: mappingPa
     from .rotate import projection_of
     perm, rot, par, projection = projection_of(projection, param)   # cic_interpolation.jl:331-345
     proj = None if (perm is None and rot is None) else (perm, rot)
-    import torch.distributed as dist
-    par_ok = bool(parallel) and dist.is_available() and dist.is_initialized()
+    par_ok, dist = False, None
+    if parallel:
+        # torch is plumbing for the multi-process path only: serial use must work with numpy + ctypes alone
+        try:
+            import torch.distributed as dist
+            par_ok = dist.is_available() and dist.is_initialized()
+        except ImportError:
+            par_ok = False
     m = sphMapping(pos, hsml, mass, rho, bin_q, weights, RM, param=par, kernel=kernel, show_progress=show_progress,
                    parallel=par_ok, reduce_image=reduce_image, calc_mean=calc_mean, sort_z=sort_z, stokes=stokes,
                    _projection=proj)

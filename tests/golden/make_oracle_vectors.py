@@ -39,6 +39,14 @@ def main():
     out["hp_pos"] = hp
     out["hp_map"] = a
     out["hp_wmap"] = wm
+    # the same particles through the extended-precision arbiter (oracle/s2g_oracle_exact.c, long double, one thread):
+    # the yardstick the CUDA maps are held to (the literal Float64 acos form above is 1e-9 away from it at Nside 16)
+    ea, ew, est = orc.healpix_deposit(hp, hsml * 12.0, m, rho, q, w, nside, "WendlandC4", 2, True, n_workers=1,
+                                      exact="sens")
+    out["hp_map_exact"] = ea
+    out["hp_wmap_exact"] = ew
+    out["hp_sens"] = est["sens"]
+    out["hp_sens_q"] = est["sens_q"]
     out["cic3d"] = orc.stencil_deposit(2, 3, pos, q, npix3 / 10.0, npix3, False)
     out["tsc2d"] = orc.stencil_deposit(3, 2, pos, q, npix2 / 10.0, npix2, True)
     # ordered Stokes/Faraday compositing (cic_mapping_2D with RM, stokes=true): particles far -> near, RM*pw = O(1) rad

@@ -10,7 +10,7 @@ import math
 import numpy as np
 import pytest
 
-from util import assert_parity, random_particles
+from util import assert_healpix_parity, assert_parity, ncores, random_particles
 
 
 # ------------------------------------------------------------------ CPU: host logic of the shard map
@@ -210,8 +210,9 @@ def test_group_healpix_map_selection_is_global(s2g, oracle):
             assert np.array_equal(wm > 0, sw > 0), "same set of touched pixels as the single call"
             assert_parity(wm, sw, rtol=1e-11, what=f"group healpix weights vs single, shell {rl}")
             assert_parity(a, sa, rtol=1e-11, what=f"group healpix map vs single, shell {rl}")
-            assert_parity(wm, rw, rtol=1e-9, what=f"group healpix weights vs oracle, shell {rl}")
-            assert_parity(a, ra, rtol=1e-9, what=f"group healpix map vs oracle, shell {rl}")
+            ea, ew, est = oracle.healpix_map(pos.copy(), hsml, m, rho, q, w, center=center, radius_limits=rl, nside=64,
+                                             kernel="WendlandC4", exact="sens", n_workers=ncores())
+            assert_healpix_parity(a, wm, ea, ew, est, what=f"group healpix vs extended precision, shell {rl}")
             assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12)
         grp.close()
 

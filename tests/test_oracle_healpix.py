@@ -197,3 +197,53 @@ def test_c_vs_python_mirror_healpix_deposit(oracle, kernel, nside):
             # for a particle 1e-3 rad from a pixel centre at Nside 16
             assert np.max(np.abs(x - y) / den) < 2e-9
             assert np.array_equal(x == 0, y == 0)      # same pixel sets
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Which Float64 evaluation is right?  The extended-precision arbiter (oracle/s2g_oracle_exact.c) settles it on the CPU.
+# ------------------------------------------------------------------------------------------------------------------
+def test_arbiter_long_double_agrees_with_float128(oracle):
+    """long double chord form == __float128 literal acos(min(d/r,1)) to the resolution of long double unit vectors
+    (5e-20 rad absolute), i.e. both are 'the exact angle' at the 1e-10 bar; the literal expression in Float64 is not."""
+    rng = np.random.default_rng(17)
+    L = oracle.lib()
+    for nside, bound64 in ((32, 1e-11), (256, 1e-10), (2048, 1e-9)):
+        worst_ld, worst_64 = 0.0, 0.0
+        for _ in range(400):
+            v = rng.normal(size=3); v *= rng.uniform(0.1, 3.0) / np.linalg.norm(v)
+            th, ph = np.arccos(v[2] / np.linalg.norm(v)), np.arctan2(v[1], v[0]) % (2 * np.pi)
+            pix = L.s2go_hp_ang2pix_ring(nside, th, ph)          # the pixel holding the particle: the smallest dx
+            _, raw = oracle.hp_angdist_exact(nside, pix, v)
+            c = np.zeros(3); L.s2go_hp_pix2vec_ring(nside, pix, c.ctypes.data_as(oracle._dp))
+            f64 = np.arccos(min(np.dot(v, c) / np.sqrt(np.sum(v * v)), 1.0))   # distance_to_pixel_center, literally
+            worst_ld = max(worst_ld, abs(float((raw[0] - raw[1]) / raw[1])))
+            worst_64 = max(worst_64, abs(float((np.longdouble(f64) - raw[1]) / raw[1])))
+        assert worst_ld < 1e-12, (nside, worst_ld)
+        assert worst_64 > bound64, (nside, worst_64)   # the acos form loses eps/dx^2
+
+
+@pytest.mark.parametrize("nside", [32, 256, 2048])
+def test_conditioning_study(oracle, nside):
+    """Sparse particles from 0.1 to 400 pixels across, WendlandC4.  Against the extended-precision maps:
+      * the Float64 CHORD formulation (what csrc/s2g_healpix*.cu evaluate; here on the CPU) meets
+        |x - exact| <= 1e-10 max(|x|,|exact|) + 4 ulp * sens on EVERY pixel, with no absolute floor;
+      * the literal Float64 acos form (pixel_weights.jl:16-22 as written, oracle/s2g_oracle.c) misses that bar on
+        thousands of pixels at Nside >= 256, by up to 1e-7 .. 1e-5 — it is the 1e-8 side of the old 5e-8 allowance."""
+    from util import hp_violations
+    rng = np.random.default_rng(1)
+    n = 2000
+    pos = rng.normal(size=(n, 3)); pos *= (rng.uniform(0.5, 2.0, n) / np.linalg.norm(pos, axis=1))[:, None]
+    hs = 10 ** rng.uniform(-4, -1, n)
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 1e4
+    a, w, st = oracle.healpix_deposit(pos, hs, m, rho, q, rho, nside, "WendlandC4")
+    ea, ew, est = oracle.healpix_deposit(pos, hs, m, rho, q, rho, nside, "WendlandC4", exact="sens", n_workers=4)
+    ca, cw = oracle.healpix_deposit_chord64(pos, hs, m, rho, q, rho, nside, "WendlandC4")
+    for k in ("n_mapped", "footprint_pixels", "n_fallback"):
+        assert st[k] == est[k]
+    assert hp_violations(cw, ew, est["sens"], ulps=4.0)[0] == 0
+    assert hp_violations(ca, ea, est["sens_q"], ulps=4.0)[0] == 0
+    nbad, worst = hp_violations(w, ew, est["sens"], ulps=8.0)
+    if nside >= 256:
+        assert nbad > 100 and worst > 1e-8, (nbad, worst)
+    # and the literal form is still "the same map" at its own conditioning level
+    assert worst < 1e-4
