@@ -35,6 +35,7 @@ def build(force: bool = False) -> str:
 
 _libs = {}
 _which = "checker"
+_fast_path = None
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int64)
@@ -49,11 +50,19 @@ def select_library(which="checker", native=True):
     global _which
     if which not in ("checker", "fast"):
         raise ValueError(which)
+    global _fast_path
     if which == "fast" and "fast" not in _libs and native:
+        # built OUTSIDE the tree: a -march=native binary must not travel to another host with the repo snapshot
+        import tempfile
+        out = os.path.join(tempfile.gettempdir(), "libs2g_oracle_fast_native_%d.so" % os.getuid())
         try:
-            subprocess.run(["make", "-C", _HERE, "fast", "FAST_ARCH=-march=native"], check=True, capture_output=True)
+            subprocess.run(["/usr/bin/gcc", "-O3", "-march=native", "-std=gnu11", "-fPIC", "-fno-fast-math",
+                            "-fvisibility=hidden", "-fopenmp", "-shared", "-o", out,
+                            os.path.join(_HERE, "s2g_oracle.c"), os.path.join(_HERE, "s2g_oracle_exact.c"),
+                            "-lquadmath", "-lm"], check=True, capture_output=True)
+            _fast_path = out
         except Exception:
-            pass
+            _fast_path = None
     _which = which
     return lib()
 
@@ -64,7 +73,7 @@ def lib():
             build()
             path = _LIB_PATH
         else:
-            path = os.path.join(_HERE, "libs2g_oracle_fast.so")
+            path = _fast_path or os.path.join(_HERE, "libs2g_oracle_fast.so")
             if not os.path.exists(path):
                 subprocess.run(["make", "-C", _HERE, "fast"], check=True, capture_output=True)
         L = C.CDLL(path)
