@@ -289,3 +289,75 @@ def test_healpix_cooperative_heavy_particles(s2g, oracle, coop_rings, monkeypatc
                                              n_workers=ncores(), exact="sens")
         assert_healpix_parity(a, wm, ea, ew, est, what=f"coop={coop_rings}")
         assert math.isclose(wm.sum(), rw.sum(), rel_tol=1e-12) and math.isclose(a.sum(), ra.sum(), rel_tol=1e-12)
+
+
+# ---------------------------------------------------------------- HEALPix tile-gather (csrc/s2g_hpgather.cu)
+@pytest.mark.parametrize("nside,kernel", [(64, "WendlandC4"), (256, "WendlandC4"), (256, "Cubic"), (256, "Quintic"),
+                                          (256, "WendlandC2"), (256, "WendlandC6"), (256, "WendlandC8"),
+                                          (2048, "WendlandC4")])
+def test_healpix_tile_gather(s2g, oracle, nside, kernel, monkeypatch):
+    """Pass B as a tile-gather (band of 16 rings x sector of <= 64 pixels owned by a CTA, pixels in registers, no
+    atomics in the inner loop): same counters as the oracle, maps at the bar of the extended-precision arbiter, for
+    discs from 3 to ~100 pixels radius incl. discs next to the poles, across phi = 0 and in the polar caps; particles
+    the gather cannot take (sub-pixel discs, discs over a pole, fallback branch) fall back to the scatter walk."""
+    monkeypatch.setenv("S2G_HP_GATHER_MIN_PIXELS", "3")
+    rng = np.random.default_rng(nside + len(kernel))
+    n = 3000 if nside < 2048 else 1200
+    ang = math.sqrt(4 * math.pi / (12 * nside * nside))
+    pos = rng.normal(size=(n, 3)) * 50.0
+    # special directions: next to the poles, across phi = 0 / 2 pi, inside the polar caps
+    pos[:8] = [[0.3, 0.1, 40.0], [-0.2, 0.3, -40.0], [30.0, 1e-9, 1.0], [30.0, -1e-9, -2.0], [25.0, 0.01, 20.0],
+               [5.0, -0.02, 30.0], [-3.0, 0.0, 35.0], [1.0, 1.0, -33.0]]
+    dist = np.linalg.norm(pos, axis=1)
+    rad = ang * rng.uniform(3.0, 40.0, n)
+    rad[:200] = ang * rng.uniform(40.0, 110.0, 200)          # large discs, many bands and sectors
+    rad[200:260] = ang * rng.uniform(0.05, 2.0, 60)          # sub-pixel / barely resolved: scatter walk
+    rad = np.minimum(rad, 0.19)
+    hsml = dist * np.sin(rad)
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 1e4; w = rng.random(n) + 0.5
+    q[300:320] = 0.0
+    for calc_mean in (True, False):
+        a, wm, st = s2g.healpix_deposit(pos, hsml, m, rho, q, w, nside, kern(s2g, kernel), calc_mean, return_stats=True)
+        ra, rw, ost = oracle.healpix_deposit(pos, hsml, m, rho, q, w, nside, kernel, 2, calc_mean)
+        assert st["n_pairs"] > 0, "the tile-gather did not run"
+        for k in ("n_mapped", "n_fallback", "touched_pixels"):
+            assert st[k] == ost[k], (k, st[k], ost[k])
+        ea, ew, est = oracle.healpix_deposit(pos, hsml, m, rho, q, w, nside, kernel, 2, calc_mean, n_workers=ncores(),
+                                             exact="sens")
+        assert_healpix_parity(a, wm, ea, ew, est, what=f"tile-gather nside={nside} {kernel}")
+        assert math.isclose(wm.sum(), ew.sum(), rel_tol=1e-12) and math.isclose(a.sum(), ea.sum(), rel_tol=1e-12)
+    # gather on == gather off (scatter walk only) to rounding
+    monkeypatch.setenv("S2G_HP_GATHER", "0")
+    a0, w0, st0 = s2g.healpix_deposit(pos, hsml, m, rho, q, w, nside, kern(s2g, kernel), False, return_stats=True)
+    assert st0["n_pairs"] == 0
+    assert_healpix_parity(a0, w0, ea, ew, est, what="scatter walk")
+
+
+def test_healpix_tile_gather_slices(s2g, oracle, monkeypatch):
+    """The gather list is walked in slices (S2G_HP_BATCH_PARTICLES) and a slice is halved when its pair count exceeds
+    S2G_PAIR_CAP: same maps and counters whatever the slicing."""
+    monkeypatch.setenv("S2G_HP_GATHER_MIN_PIXELS", "3")
+    nside = 128
+    rng = np.random.default_rng(77)
+    n = 6000
+    ang = math.sqrt(4 * math.pi / (12 * nside * nside))
+    pos = rng.normal(size=(n, 3)) * 50.0
+    dist = np.linalg.norm(pos, axis=1)
+    hsml = dist * np.sin(ang * rng.uniform(3.0, 30.0, n))
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 1e4; w = rng.random(n) + 0.5
+    ref = None
+    for batch, cap in (("100000000", "1000000000"), ("1500", "1000000000"), ("4096", "3000")):
+        monkeypatch.setenv("S2G_HP_BATCH_PARTICLES", batch)
+        monkeypatch.setenv("S2G_PAIR_CAP", cap)
+        a, wm, st = s2g.healpix_deposit(pos, hsml, m, rho, q, w, nside, s2g.WendlandC4(2), True, return_stats=True)
+        if ref is None:
+            ref = (a, wm, st)
+            ea, ew, est = oracle.healpix_deposit(pos, hsml, m, rho, q, w, nside, "WendlandC4", 2, True,
+                                                 n_workers=ncores(), exact="sens")
+            assert_healpix_parity(a, wm, ea, ew, est, what="one slice")
+            assert st["touched_pixels"] == est["touched_pixels"] and st["n_mapped"] == est["n_mapped"]
+        else:
+            for k in ("n_mapped", "n_fallback", "touched_pixels", "n_pairs"):
+                assert st[k] == ref[2][k], (k, batch, cap)
+            assert_parity(wm, ref[1], rtol=1e-12, what=f"slices {batch}/{cap}")
+            assert_parity(a, ref[0], rtol=1e-12, what=f"slices {batch}/{cap}")
