@@ -218,6 +218,7 @@ __global__ void k_footprints3d(s2g_particles P, s2g_geom G, long long* __restric
 
 int s2g_launch_footprints(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int dims, long long* out)
 {
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     if (P.n <= 0) return S2G_OK;
     const int blocks = (int)((P.n + 255) / 256);
     if (dims == 2)
@@ -297,6 +298,7 @@ __global__ void k_center_filter(s2g_particles P, void* __restrict__ pos_out, uin
 
 int s2g_launch_center_filter(s2g_ctx* ctx, const s2g_particles& P, void* pos_out, uint8_t* mask)
 {
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     if (P.n <= 0) return S2G_OK;
     const int blocks = (int)((P.n + 255) / 256);
     k_center_filter<<<blocks, 256, 0, ctx->stream>>>(P, pos_out, mask);

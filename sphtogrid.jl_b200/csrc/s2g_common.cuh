@@ -65,7 +65,15 @@ struct s2g_ctx {
     std::vector<timer> timers;
     size_t timers_used = 0;
     int launches = 0;  // kernels of this library launched since stats_begin (cub kernels counted as one each)
+    struct s2g_stager* stager = nullptr;  // overlapped host->device staging of the current call (s2g_api.cu)
 };
+
+// Host->device staging that overlaps the deposit: a helper thread copies the caller's (pageable) arrays chunk by chunk
+// on its own stream and records an event per chunk; the deposit calls s2g_stage_wait(ctx, upto) before the first
+// kernel that reads particles [0, upto) — a no-op when the call's inputs are already on the device.
+int s2g_stage_wait(s2g_ctx* ctx, long long upto);
+// first slice of a sliced deposit while a staging thread runs (small, so that the deposit starts early); 0 = no limit
+long long s2g_stage_first_slice(const s2g_ctx* ctx);
 
 enum { PH_PREP = 0, PH_SORT = 1, PH_NORM = 2, PH_DEPOSIT = 3, PH_EPILOGUE = 4, PH_N = 5 };
 // records the start of a phase; returns a handle for s2g_phase_end

@@ -680,6 +680,7 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
     default: s2g_set_error("unknown kernel id %d", kernel); return S2G_EINVAL;
     }
     if (ctx->strategy == S2G_STRATEGY_SCATTER) {
+        S2G_TRY(s2g_stage_wait(ctx, P.n));
         const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
         const int rc = s2g_launch_scatter_2d(ctx, P, G, kernel, nullptr, P.n, image);
         s2g_phase_end(ctx, ph);
@@ -698,7 +699,11 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
     long long p0 = 0;
     long long batch = min(batch_max, P.n);
     while (p0 < P.n) {
-        const long long nb = min(batch, P.n - p0);
+        long long nb = min(batch, P.n - p0);
+        // overlapped staging (s2g_api.cu): a small first slice lets the deposit start while the rest is still copied;
+        // every slice waits for exactly the particles it reads
+        if (p0 == 0 && s2g_stage_first_slice(ctx) > 0) nb = min(nb, s2g_stage_first_slice(ctx));
+        S2G_TRY(s2g_stage_wait(ctx, p0 + nb));
         void *d_cls, *d_np, *d_ps, *d_pg, *d_ls, *d_lg, *d_tmp, *d_sum;
         S2G_TRY(s2g_scratch(ctx, "g_cls", sizeof(int) * (nb + 1), &d_cls));
         S2G_TRY(s2g_scratch(ctx, "g_np", sizeof(unsigned) * (nb + 1), &d_np));

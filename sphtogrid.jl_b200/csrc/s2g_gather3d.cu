@@ -530,6 +530,7 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
 int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image)
 {
     if (P.n <= 0) return S2G_OK;
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     switch (kernel) {
     case S2G_KERNEL_CUBIC: return deposit3d_k<S2G_KERNEL_CUBIC>(ctx, P, G, image);
     case S2G_KERNEL_QUINTIC: return deposit3d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, image);

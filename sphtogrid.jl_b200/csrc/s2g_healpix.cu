@@ -695,6 +695,7 @@ int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, in
                        const unsigned char* take, double* amap, double* wmap)
 {
     if (P.n <= 0) return S2G_OK;
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     switch (kernel) {
     case S2G_KERNEL_CUBIC: return launch_healpix_k<S2G_KERNEL_CUBIC>(ctx, P, nside, calc_mean, take, amap, wmap);
     case S2G_KERNEL_QUINTIC: return launch_healpix_k<S2G_KERNEL_QUINTIC>(ctx, P, nside, calc_mean, take, amap, wmap);
@@ -770,6 +771,7 @@ int s2g_hp_radii(s2g_ctx* ctx, const s2g_particles& P, double r0, double r1, uns
 {
     *n_selected = 0;
     if (P.n <= 0) return S2G_OK;
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_PAIRS, 0, sizeof(unsigned long long), ctx->stream));
     const int blocks = (int)((P.n + 255) / 256);
     const int ph = s2g_phase_begin(ctx, PH_PREP);

@@ -372,6 +372,7 @@ int run_stokes(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const do
 int s2g_launch_stokes_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const double* rm_dev,
                          double* image)
 {
+    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     if (P.n <= 0) return S2G_OK;
     switch (kernel) {
     case S2G_KERNEL_CUBIC: return run_stokes<S2G_KERNEL_CUBIC>(ctx, P, G, rm_dev, image);
