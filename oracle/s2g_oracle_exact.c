@@ -39,6 +39,11 @@ static const ld PI_L = 3.14159265358979323846264338327950288L;
 #define PI_Q 3.14159265358979323846264338327950288419716939937510Q
 
 /* ring (1..4nside-1) and 1-based in-ring index of a RING pixel; exact integer arithmetic */
+static void pix_ring_iphi(int64_t nside, int64_t pix, int64_t* ring, int64_t* iphi, int64_t* nr, int* off_half);
+void s2go_exact_ring_of(int64_t nside, int64_t pix, int64_t* ring, int64_t* iphi, int64_t* nr, int* off_half)
+{
+    pix_ring_iphi(nside, pix, ring, iphi, nr, off_half);
+}
 static void pix_ring_iphi(int64_t nside, int64_t pix, int64_t* ring, int64_t* iphi, int64_t* nr, int* off_half)
 {
     const int64_t npix = 12 * nside * nside, ncap = 2 * nside * (nside - 1), nl4 = 4 * nside;
@@ -59,6 +64,54 @@ static void pix_ring_iphi(int64_t nside, int64_t pix, int64_t* ring, int64_t* ip
         *ring = nl4 - r; *nr = 4 * r; *off_half = 1;
         *iphi = pix - (npix - 2 * r * (r + 1)) + 1;
     }
+}
+
+/* walker over a pixel list: consecutive pixels of one ring share (sinθ, cosθ) and step the azimuth by a rotation
+ * (exact sinl/cosl re-seed every 32 steps: the recurrence adds < 1e-18); anything else is computed from scratch */
+typedef struct {
+    int64_t nside, last_pix, ring, nr;
+    int steps;
+    ld st, ct, cphi, sphi, cd, sd;
+} pixwalk;
+
+static void pix2vec_l(int64_t nside, int64_t pix, ld c[3]);
+
+static void walk_init(pixwalk* w, int64_t nside)
+{
+    w->nside = nside; w->last_pix = -10; w->steps = 0; w->ring = -1; w->nr = 0;
+    w->st = w->ct = w->cphi = w->sphi = w->cd = w->sd = 0.0L;
+}
+
+static void walk_vec(pixwalk* w, int64_t pix, ld c[3])
+{
+    if (pix == w->last_pix + 1 && w->steps < 32) {
+        /* same ring?  the next pixel number stays in the ring unless last_pix was the ring's last pixel */
+        int64_t ring, iphi, nr; int oh;
+        (void)oh;
+        /* cheap test: recompute ring only at ring boundaries, detected through the cached ring extent */
+        if (w->ring >= 0 && pix < w->nr /* nr holds the first pixel of the NEXT ring here */) {
+            const ld cn = w->cphi * w->cd - w->sphi * w->sd, sn = w->sphi * w->cd + w->cphi * w->sd;
+            w->cphi = cn; w->sphi = sn; w->last_pix = pix; w->steps++;
+            c[0] = w->st * cn; c[1] = w->st * sn; c[2] = w->ct;
+            return;
+        }
+        (void)ring; (void)iphi; (void)nr;
+    }
+    /* from scratch */
+    int64_t ring, iphi, nr; int oh;
+    extern void s2go_exact_ring_of(int64_t, int64_t, int64_t*, int64_t*, int64_t*, int*);
+    s2go_exact_ring_of(w->nside, pix, &ring, &iphi, &nr, &oh);
+    pix2vec_l(w->nside, pix, c);
+    const ld n = (ld)w->nside;
+    (void)n;
+    w->ct = c[2];
+    w->st = sqrtl(c[0] * c[0] + c[1] * c[1]);
+    if (w->st > 0) { w->cphi = c[0] / w->st; w->sphi = c[1] / w->st; } else { w->cphi = 1; w->sphi = 0; }
+    const ld dphi = 2.0L * 3.14159265358979323846264338327950288L / (ld)nr;
+    w->cd = cosl(dphi); w->sd = sinl(dphi);
+    w->ring = ring;
+    w->nr = pix - (iphi - 1) + nr;   /* first pixel of the next ring */
+    w->last_pix = pix; w->steps = 0;
 }
 
 /* exact pixel centre (unit vector), long double */
@@ -128,6 +181,13 @@ S2GO_API void s2go_hp_angdist_exact(int64_t nside, int64_t pix, const double pos
     if (out_ld) { out_ld[0] = dx_l; out_ld[1] = (ld)dx_q; out_ld[2] = acosl(tl); }
 }
 
+static inline ld ipow(ld t, int n)
+{
+    ld r = 1.0L;
+    for (int i = 0; i < n; i++) r *= t;
+    return r;
+}
+
 static ld shape_l(int kid, ld u)
 {
     if (!(u < 1.0L)) return 0.0L;
@@ -137,19 +197,16 @@ static ld shape_l(int kid, ld u)
     case 1: {
         ld b = 2.0L / 3.0L - u, c = 1.0L / 3.0L - u;
         b = b > 0 ? b : 0; c = c > 0 ? c : 0;
-        return powl(t, 5) - 6.0L * powl(b, 5) + 15.0L * powl(c, 5);
+        return ipow(t, 5) - 6.0L * ipow(b, 5) + 15.0L * ipow(c, 5);
     }
-    case 2: return powl(t, 4) * (1.0L + 4.0L * u);
-    case 3: return powl(t, 6) * (1.0L + 6.0L * u + (35.0L / 3.0L) * u * u);
-    case 4: return powl(t, 8) * (1.0L + 8.0L * u + 25.0L * u * u + 32.0L * u * u * u);
-    case 5: return powl(t, 10) * (5.0L + 50.0L * u + 210.0L * u * u + 450.0L * u * u * u + 429.0L * u * u * u * u);
+    case 2: return ipow(t, 4) * (1.0L + 4.0L * u);
+    case 3: return ipow(t, 6) * (1.0L + 6.0L * u + (35.0L / 3.0L) * u * u);
+    case 4: return ipow(t, 8) * (1.0L + 8.0L * u + 25.0L * u * u + 32.0L * u * u * u);
+    case 5: return ipow(t, 10) * (5.0L + 50.0L * u + 210.0L * u * u + 450.0L * u * u * u + 429.0L * u * u * u * u);
     }
     return 0.0L;
 }
 
-/* healpix particle loop (main.jl:143-213) with weight_per_index / calculate_weights in long double.
- * Same signature as s2go_healpix_deposit; maps are accumulated with `omp atomic` when n_workers > 1 (the order of the
- * Float64 additions into a pixel then varies at the 1e-16 level — irrelevant at the 1e-10 bar). */
 /* `sens_map` (optional, may be NULL; 2*npix doubles: weight map first, then quantity map): Σ over the contributions to a pixel of |∂(pix_weight)/∂dx| · 1 rad, i.e. how much
  * the exact weight-map value moves per radian of error in the angular distances.  Multiplied by the resolution of
  * Float64 unit vectors (a few ulp of 1 = a few 1e-16 rad) it is the part of a pixel value that NO Float64 evaluation
@@ -170,6 +227,7 @@ S2GO_API int s2go_healpix_deposit_exact(const double* pos, const double* hsml, c
         int64_t* pixidx = (int64_t*)malloc(sizeof(int64_t) * (size_t)cap);
         ld* wk = (ld*)malloc(sizeof(ld) * (size_t)cap);
         ld* A = (ld*)malloc(sizeof(ld) * (size_t)cap);
+        ld* D = (ld*)malloc(sizeof(ld) * (size_t)cap);
 #pragma omp for schedule(dynamic, 16)
         for (int64_t ip = 0; ip < n; ip++) {
             if (!calc_mean && binq[ip] == 0.0) continue;
@@ -188,6 +246,7 @@ S2GO_API int s2go_healpix_deposit_exact(const double* pos, const double* hsml, c
                 pixidx = (int64_t*)realloc(pixidx, sizeof(int64_t) * (size_t)cap);
                 wk = (ld*)realloc(wk, sizeof(ld) * (size_t)cap);
                 A = (ld*)realloc(A, sizeof(ld) * (size_t)cap);
+                D = (ld*)realloc(D, sizeof(ld) * (size_t)cap);
             }
             const ld Dx = sqrtl((ld)P[0] * P[0] + (ld)P[1] * P[1] + (ld)P[2] * P[2]);
             const ld ph = asinl((ld)hsml[ip] / Dx), hinv = 1.0L / ph;
@@ -198,9 +257,11 @@ S2GO_API int s2go_healpix_deposit_exact(const double* pos, const double* hsml, c
             dz /= aD * aD;
             int64_t n_distr = 0, n_tot = 0;
             ld dw = 0.0L, da = 0.0L;
+            pixwalk wlk;
+            walk_init(&wlk, nside);
             for (int64_t k = 0; k < np; k++) {
                 ld c[3];
-                pix2vec_l(nside, pixidx[k], c);
+                walk_vec(&wlk, pixidx[k], c);
                 const ld ex = ux - c[0], ey = uy - c[1], ez = uz - c[2];
                 const ld hc = 0.5L * sqrtl(ex * ex + ey * ey + ez * ez);
                 const ld ddx = 2.0L * asinl(hc < 1.0L ? hc : 1.0L);
@@ -213,16 +274,13 @@ S2GO_API int s2go_healpix_deposit_exact(const double* pos, const double* hsml, c
                 ld w_ = 0.0L;
                 if (u <= 1.0L) { w_ = shape_l(kid, u); dw += w_ * a_; n_distr++; } /* the kernel norm cancels (Q14) */
                 A[k] = a_; wk[k] = w_;
+                if (sens_map) D[k] = ddx;
             }
             ld* dA = NULL; ld* dW = NULL;
             if (sens_map) { /* second sweep: derivatives of A and w with respect to dx (cheap: sens is a test aid) */
                 dA = (ld*)malloc(sizeof(ld) * (size_t)np); dW = (ld*)malloc(sizeof(ld) * (size_t)np);
                 for (int64_t k = 0; k < np; k++) {
-                    ld c[3];
-                    pix2vec_l(nside, pixidx[k], c);
-                    const ld ex = ux - c[0], ey = uy - c[1], ez = uz - c[2];
-                    const ld hc = 0.5L * sqrtl(ex * ex + ey * ey + ez * ez);
-                    const ld ddx = 2.0L * asinl(hc < 1.0L ? hc : 1.0L);
+                    const ld ddx = D[k];
                     const ld u = ddx * hinv, h = 1e-7L;
                     const ld inner = fabsl(ph - (ddx - 0.5L * ang_pix));
                     dA[k] = (inner < ang_pix) ? 1.0L / ang_pix / (aD * aD) : 0.0L;
@@ -259,7 +317,7 @@ S2GO_API int s2go_healpix_deposit_exact(const double* pos, const double* hsml, c
             free(dA); free(dW);
             s_mapped++; s_foot += np;
         }
-        free(pixidx); free(wk); free(A);
+        free(pixidx); free(wk); free(A); free(D);
     }
     if (stats4) { stats4[0] = s_mapped; stats4[1] = s_foot; stats4[2] = s_foot; stats4[3] = s_fb; }
     return 0;

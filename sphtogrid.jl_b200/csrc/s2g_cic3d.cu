@@ -10,10 +10,18 @@
 // lanes: W wide along k (contiguous axis, indices.jl:15-17), 32/W deep along j; i is walked by the whole warp in groups
 // of four independent chains.  Coordinates in units of h: a cell centre is inside the kernel iff a²+b²+c² < 1
 // (the reference's u = sqrt(dx²+dy²+dz²)·h⁻¹ <= 1 up to the last ulp at the rim, where w -> 0 anyway).
+// S3_CAP: per-warp capacity of the shared-memory cell list.  Pass A stores the weight wk·dV and the packed box
+// coordinates of every cell with a non-zero weight (warp-level compaction: ballot + prefix popcount, in the lanes'
+// k-contiguous order), so that pass B neither re-evaluates the kernel (cic_3D.jl:172-188 recomputes nothing either:
+// the reference keeps wk[] and V[] from calculate_weights) nor walks the empty corners of the bounding box: all 32
+// lanes issue reds.  A particle with more non-zero cells than S3_CAP (h > ~6 cells) takes the two-pass path.
+constexpr int S3_CAP = 1024;
+
 template <int KID>
 __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G, int lane,
                                                 double* __restrict__ image, unsigned long long& touched,
-                                                unsigned long long& fallback)
+                                                unsigned long long& fallback, double* __restrict__ s_w,
+                                                unsigned* __restrict__ s_c)
 {
     const int ni = r.hi[0] - r.lo[0] + 1, nj = r.hi[1] - r.lo[1] + 1, nk = r.hi[2] - r.lo[2] + 1;
     const int lw = nk >= 32 ? 5 : (nk <= 1 ? 0 : 32 - __clz(nk - 1));
@@ -26,19 +34,27 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     const double hinv = r.hinv;
     const double xb = center_dist(r.x, (double)r.lo[0]) * hinv;  // a of the first i-plane
 
-    // ---- pass A (calculate_weights, cic_3D.jl:13-78)
+    // ---- pass A (calculate_weights, cic_3D.jl:13-78); loops are warp-uniform (lanes without a column idle) so that
+    // the list compaction can ballot
     double sw = 0.0;
     int cnt = 0;
-    for (int kc = c0; kc < nk; kc += W) {
+    bool cache = (s_w != nullptr) && ni < 256 && nj < 256 && nk < 256;
+    int n_list = 0;                 // uniform
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int kb = 0; kb < nk; kb += W) {
+        const int kc = kb + c0;
         const int k = r.lo[2] + kc;
         const double cz = center_dist(r.z, (double)k) * hinv;
         const double dz = (k == r.lo[2]) ? dz_lo : ((k == r.hi[2]) ? dz_hi : 1.0);
-        for (int jr = r0; jr < nj; jr += R) {
+        for (int jb = 0; jb < nj; jb += R) {
+            const int jr = jb + r0;
             const int j = r.lo[1] + jr;
             const double by = center_dist(r.y, (double)j) * hinv;
             const double bc2 = fma(by, by, cz * cz) + 1e-300;  // > 0 even when a cell centre sits on the particle
-            if (bc2 >= 1.0) continue;
+            const bool colv = (kc < nk) && (jr < nj) && (bc2 < 1.0);
+            if (!__any_sync(0xffffffffu, colv)) continue;
             const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
+            const double dydz = dy * dz;
             double col = 0.0;
             for (int ii = 0; ii < ni; ii += 4) {
                 double wk[4];
@@ -47,20 +63,33 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                 for (int q = 0; q < 4; ++q) {
                     const double a = fma(-(double)(ii + q), hinv, xb);
                     const double s = fma(a, a, bc2);
-                    in[q] = below_one(s) && (ii + q < ni);
+                    in[q] = colv && below_one(s) && (ii + q < ni);
                     wk[q] = shape_s<KID>(s);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = r.lo[0] + ii + q;
                     const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
-                    col = fma(select_or_zero(in[q], wk[q]), dx, col);
+                    const double wq = select_or_zero(in[q], wk[q]);
+                    col = fma(wq, dx, col);
                     cnt += in[q] ? 1 : 0;
+                    if (cache) {
+                        const double gq = wq * (dx * dydz);     // the cell's wk·dV of pass B
+                        const bool live = nonzero_bits(gq);
+                        const unsigned m = __ballot_sync(0xffffffffu, live);
+                        const int pos = n_list + __popc(m & lt_mask);
+                        if (live && pos < S3_CAP) {
+                            s_w[pos] = gq;
+                            s_c[pos] = ((unsigned)(ii + q) << 16) | ((unsigned)jr << 8) | (unsigned)kc;
+                        }
+                        n_list += __popc(m);
+                    }
                 }
             }
-            sw = fma(col, dy * dz, sw);
+            sw = fma(col, dydz, sw);
         }
     }
+    cache = cache && n_list <= S3_CAP;
     sw = warp_sum(sw);
     cnt = __reduce_add_sync(0xffffffffu, cnt);
 
@@ -126,6 +155,21 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     }
     const double vq = volume_norm * r.q;
     const bool live_p = nonzero_bits(volume_norm);
+    if (cache) {
+        if (!live_p) return;
+        __syncwarp();
+        const long long o0 = (long long)r.lo[0] * n * n + (long long)r.lo[1] * n + r.lo[2];
+        for (int t = lane; t < n_list; t += 32) {
+            const double g = s_w[t];
+            const unsigned c = s_c[t];
+            const long long idx = o0 + (long long)(c >> 16) * n * n + (long long)((c >> 8) & 255u) * n + (c & 255u);
+            red_add(image + npl + idx, g * volume_norm);
+            red_add(image + idx, g * vq);
+        }
+        if (lane == 0) touched += (unsigned long long)n_list;
+        __syncwarp();   // the list is reused by the next particle
+        return;
+    }
     for (int kc = c0; kc < nk; kc += W) {
         const int k = r.lo[2] + kc;
         const double cz = center_dist(r.z, (double)k) * hinv;
@@ -169,9 +213,16 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
 template <int KID>
 __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, const unsigned* __restrict__ order,
                                                    long long n_list, double* __restrict__ image,
-                                                   unsigned long long* __restrict__ counters)
+                                                   unsigned long long* __restrict__ counters, int use_cache)
 {
     const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char s3_smem[];
+    double* s_w = nullptr;
+    unsigned* s_c = nullptr;
+    if (use_cache) {
+        s_w = reinterpret_cast<double*>(s3_smem) + (threadIdx.x >> 5) * S3_CAP;
+        s_c = reinterpret_cast<unsigned*>(s3_smem + 8 * S3_CAP * sizeof(double)) + (threadIdx.x >> 5) * S3_CAP;
+    }
     unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
     constexpr int CHUNK = 4;
     for (;;) {
@@ -189,7 +240,7 @@ __global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, 
                 fpx += (unsigned long long)(r.hi[0] - r.lo[0] + 1) * (unsigned long long)(r.hi[1] - r.lo[1] + 1) *
                        (unsigned long long)(r.hi[2] - r.lo[2] + 1);
             }
-            warp_deposit_3d<KID>(r, G, lane, image, touched, fallback);
+            warp_deposit_3d<KID>(r, G, lane, image, touched, fallback, s_w, s_c);
         }
     }
     touched = (unsigned long long)warp_sum_ll((long long)touched);
@@ -256,8 +307,17 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
     const int warps_needed = (int)std::min<long long>((n_list + 3) / 4, (long long)ctx->sm_count * 8 * 8);
     int blocks = max(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
+    // shared-memory cell lists (S3_CAP entries of 12 bytes per warp = 96 KB per CTA, 2 CTAs/SM); S2G_3D_CACHE=0: off
+    const char* e_c = getenv("S2G_3D_CACHE");
+    const int use_cache = e_c ? (atoi(e_c) != 0) : 1;
+    const size_t smem = use_cache ? (size_t)8 * S3_CAP * (sizeof(double) + sizeof(unsigned)) : 0;
+    static bool attr_set[64] = {};
+    if (use_cache && !attr_set[ctx->device & 63]) {
+        S2G_CUDA(cudaFuncSetAttribute(k_scatter3d<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 63] = true;
+    }
     const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
-    k_scatter3d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, order, n_list, image, ctx->d_counters);
+    k_scatter3d<KID><<<blocks, 256, smem, ctx->stream>>>(P, G, order, n_list, image, ctx->d_counters, use_cache);
     s2g_phase_end(ctx, ph);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
