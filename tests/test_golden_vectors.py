@@ -26,8 +26,10 @@ def test_oracle_reproduces_golden_vectors(oracle):
     assert np.array_equal(a, G["hp_map"]) and np.array_equal(wm, G["hp_wmap"])
     ea, ew, est = oracle.healpix_deposit(G["hp_pos"], hsml * 12.0, m, rho, q, w, 16, "WendlandC4", 2, True,
                                          n_workers=1, exact="sens")
-    # long double libm (sinl/cosl/asinl): allow an ulp-level drift of the extended type between libm builds
-    assert np.allclose(ea, G["hp_map_exact"], rtol=1e-15, atol=0) and np.allclose(ew, G["hp_wmap_exact"], rtol=1e-15, atol=0)
+    # long double libm (sinl/cosl/asinl) and the azimuth recurrence of the ring walker: allow a drift at the level of
+    # the extended type (1e-13 of a pixel value, 1e-17 of the map maximum for kernel-rim pixels)
+    for x, y in ((ea, G["hp_map_exact"]), (ew, G["hp_wmap_exact"])):
+        assert np.allclose(x, y, rtol=1e-13, atol=1e-17 * np.abs(y).max())
     assert np.array_equal(oracle.stencil_deposit(2, 3, pos, q, 2.0, 20, False), G["cic3d"])
     assert np.array_equal(oracle.stencil_deposit(3, 2, pos, q, 6.4, 64, True), G["tsc2d"])
     o = G["stokes_order"]
