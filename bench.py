@@ -370,11 +370,26 @@ def run_workload(e, name, steps, warmup, main):
             _lib.check(L.s2g_sphmap_dev(ctx.handle, dims, P(d_pos), P(d_h), P(d_m), P(d_rho), P(q_t), P(w_t), n_loc, 1,
                                         1, shift, 0, -1.0, half, float(par2.len2pix), npix, kid, 1, 0, P(image)))
 
+    from sphtogrid_b200 import distributed as sdist
+    xwork = {}
+    divide = sdist.device_divide(ctx)
+
     def step_device():
         deposit_only()
         if world > 1:
-            dist.all_reduce(image)       # image = sum(fetch.(futures)) (cic_interpolation.jl:199)
-        if healpix:
+            # image = sum(fetch.(futures)) (cic_interpolation.jl:199): the one exchange step of the path
+            if healpix or stencil:
+                dist.reduce(image, dst=0)                       # un-reduced maps go back to the master
+                return
+            # reduce-scatter per plane, reduce_image division on this rank's pixel slice, gather on the master
+            flat = sdist.exchange_reduce(image, 1, ncell, dims, True, divide, work=xwork, gather="root")
+            if rank == 0:
+                if dims == 2:   # transposition to Array(N,N,1) memory (reduce_image = 0: the division is done)
+                    _lib.check(L.s2g_reduce_image_2d_dev(ctx.handle, P(flat), npix, npix, 1, 0, P(out)))
+                else:
+                    out.copy_(flat)
+            return
+        if healpix or stencil:
             return
         if dims == 2:
             _lib.check(L.s2g_reduce_image_2d_dev(ctx.handle, P(image), npix, npix, 1, 1, P(out)))
@@ -419,6 +434,10 @@ def run_workload(e, name, steps, warmup, main):
     if world > 1:
         dist.all_reduce(cnt)
     n_mapped, fpx_all, touched_all, pairs, launches, n_in_all = [int(x) for x in cnt.tolist()]
+    fmax = torch.tensor([float(st["footprint_pixels"])], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+    imb = float(fmax[0]) / max(fpx_all / world, 1.0) - 1.0
     if stencil:
         n_mapped = n_total
     fpx, touched = int(st["footprint_pixels"]), int(st["touched_pixels"])
@@ -554,7 +573,12 @@ def run_workload(e, name, steps, warmup, main):
                              "l2": "inputs (%.2f GB/rank) larger than L2" % (n_loc * in_bytes / 1e9),
                              "mapped_particles": n_mapped, "particles_in": n_in_all, "pairs": pairs,
                              "footprint_pixels_all_ranks": fpx_all, "touched_pixels_all_ranks": touched_all,
-                             "exchange": "all_reduce(NCCL) of the flat image, then reduce_image" if world > 1 else None},
+                             "exchange": (None if world == 1 else
+                                          "reduce(NCCL) of the two un-reduced maps to rank 0" if (healpix or stencil) else
+                                          "reduce_scatter(NCCL) per plane + reduce_image division of the rank's pixel "
+                                          "slice + gather on rank 0 + transposition"),
+                             "shard": "domain_decomposition by particle id (uniform synthetic stream); work imbalance "
+                                      "max/mean - 1 = %.4f" % imb},
                   "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches * steps,
                   "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline,
                   "wall_ms_per_step": wall_step}

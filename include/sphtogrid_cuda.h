@@ -273,6 +273,15 @@ S2G_API int s2g_stencil_deposit_dev(s2g_ctx* ctx, int32_t order, int32_t dims, c
 /* ---- finite-guarded accumulation of partial maps (src/distributed_mapping/cic.jl:62-70, healpix.jl:44-52) */
 S2G_API int s2g_accumulate_finite_dev(s2g_ctx* ctx, double* sum_dev, const double* local_dev, int64_t n);
 
+/* ---- per-rank epilogue of the multi-process exchange (one process per GPU): after a reduce-scatter of the partial
+ *      flat images (`image = sum(fetch.(futures))`, src/cic_interpolation/cic_interpolation.jl:199, :256) every rank
+ *      holds the SUMMED planes of its own pixel slice and applies the reduce_image division to it
+ *      (src/cic_interpolation/reduce_image.jl:8-31 for dims 2: q /= w where reduce_image and w > 0; :39-55 for dims 3:
+ *      where q > 0, q /= (reduce_image ? w : 1)); the slices are then gathered and, in 2D, transposed by
+ *      s2g_reduce_image_2d_dev(..., reduce_image = 0, ...).  q_slice: n_images planes of plane_stride elements. */
+S2G_API int s2g_divide_slice_dev(s2g_ctx* ctx, int32_t dims, double* q_slice_dev, const double* w_slice_dev, int64_t n,
+                                 int64_t plane_stride, int32_t n_images, int32_t reduce_image);
+
 /* ---- device group: `parallel=true` of sphMapping (src/cic_interpolation/cic_interpolation.jl:171-215, 236-271) for a
  *      caller that is ONE process with several visible GPUs (a Julia session without Distributed workers).
  *      s2g_domain_decomposition  = domain_decomposition (src/parallel/domain_decomp.jl:7-17), 0-based starts; needs no

@@ -106,6 +106,7 @@ _SIGS = {
     "s2g_stencil_deposit": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _vp, C.POINTER(Stats)]),
     "s2g_stencil_deposit_dev": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f64, _i64, _i32, _i32, _vp]),
     "s2g_accumulate_finite_dev": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "s2g_divide_slice_dev": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _i32]),
     "s2g_domain_decomposition": (C.c_int, [_i64, _i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "s2g_group_init": (C.c_int, [C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
     "s2g_group_shutdown": (C.c_int, [_vp]),

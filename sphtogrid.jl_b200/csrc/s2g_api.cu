@@ -1228,6 +1228,16 @@ extern "C" int s2g_accumulate_finite_dev(s2g_ctx* ctx, double* sum_dev, const do
     return s2g_launch_accumulate_finite(ctx, sum_dev, local_dev, n);
 }
 
+extern "C" int s2g_divide_slice_dev(s2g_ctx* ctx, int32_t dims, double* q_slice_dev, const double* w_slice_dev,
+                                    int64_t n, int64_t plane_stride, int32_t n_images, int32_t reduce_image)
+{
+    CTX_ENTER(ctx);
+    S2G_CHECK(dims == 2 || dims == 3, S2G_EINVAL, "%s: dims must be 2 or 3", __func__);
+    S2G_CHECK(n >= 0 && (n == 0 || (q_slice_dev && w_slice_dev)) && n_images >= 1 && plane_stride >= n, S2G_EINVAL,
+              "%s: bad arguments", __func__);
+    return s2g_launch_divide_slice(ctx, dims, q_slice_dev, w_slice_dev, n, plane_stride, n_images, reduce_image);
+}
+
 // ------------------------------------------------------------------------------------------------
 // synthetic particles / microbenchmarks
 // ------------------------------------------------------------------------------------------------

@@ -281,6 +281,8 @@ int s2g_launch_healpix_pixels(s2g_ctx* ctx, const double pos[3], double radius, 
 int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const void* q, long long n, int in_dtype,
                        double len2pix, long long npix, int periodic, double* image_dev);
 int s2g_launch_accumulate_finite(s2g_ctx* ctx, double* sum_dev, const double* local_dev, long long n);
+int s2g_launch_divide_slice(s2g_ctx* ctx, int dims, double* q, const double* w, long long n, long long stride,
+                            int n_images, int reduce_image);
 int s2g_launch_synth(s2g_ctx* ctx, uint64_t seed, long long first_id, long long n, long long n_total, double box,
                      double n_ngb, double sigma, int out_dtype, void* pos, void* hsml, void* m, void* rho, void* temp);
 int s2g_run_microbench(s2g_ctx* ctx, int which, size_t bytes, int iters, double* rate_out);

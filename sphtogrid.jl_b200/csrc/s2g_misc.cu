@@ -115,6 +115,39 @@ int s2g_launch_accumulate_finite(s2g_ctx* ctx, double* sum, const double* local,
     return S2G_OK;
 }
 
+// reduce_image division on a pixel SLICE (the per-rank epilogue after a reduce-scatter of the partial images):
+// dims 2 (reduce_image.jl:8-31): q /= w where reduce_image and w > 0;  dims 3 (reduce_image.jl:39-55, quirk Q7): where
+// q > 0, q /= (reduce_image ? w : 1).  In place, elementwise, n_images quantity planes of `stride` elements each.
+__global__ void k_divide_slice(double* __restrict__ q, const double* __restrict__ w, long long n, long long stride,
+                               int n_images, int dims, int reduce_image)
+{
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += step) {
+        const double wv = w[e];
+        for (int k = 0; k < n_images; ++k) {
+            double v = q[k * stride + e];
+            if (dims == 2) {
+                if (reduce_image && wv > 0.0) v = v / wv;
+            } else if (v > 0.0)
+                v = v / (reduce_image ? wv : 1.0);
+            q[k * stride + e] = v;
+        }
+    }
+}
+
+int s2g_launch_divide_slice(s2g_ctx* ctx, int dims, double* q, const double* w, long long n, long long stride,
+                            int n_images, int reduce_image)
+{
+    if (n <= 0) return S2G_OK;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    const int ph = s2g_phase_begin(ctx, PH_EPILOGUE);
+    k_divide_slice<<<blocks, 256, 0, ctx->stream>>>(q, w, n, stride, n_images, dims, reduce_image);
+    s2g_phase_end(ctx, ph);
+    S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return S2G_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // synthetic Gadget-like particles: Philox4x32-10, key = seed, counter = (particle id, draw)
 // ------------------------------------------------------------------------------------------------

@@ -43,6 +43,102 @@ def allreduce_sum_(tensor):
     return tensor
 
 
+def _reduce_scatter_plane(out, plane):
+    """out (len/ws elements) = this rank's slice of the sum over ranks of `plane`."""
+    dist = _dist()
+    try:
+        dist.reduce_scatter_tensor(out, plane, op=dist.ReduceOp.SUM)
+    except (RuntimeError, NotImplementedError):
+        # backends without reduce-scatter (gloo on the CPU tests): same result through an all-reduce
+        tmp = plane.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+        r, n = dist.get_rank(), out.numel()
+        out.copy_(tmp[r * n:(r + 1) * n])
+
+
+def _all_gather_plane(out, mine):
+    dist = _dist()
+    try:
+        dist.all_gather_into_tensor(out, mine)
+    except (RuntimeError, NotImplementedError):
+        parts = [out[i * mine.numel():(i + 1) * mine.numel()] for i in range(dist.get_world_size())]
+        tmp = [torch_empty_like(mine) for _ in parts]
+        dist.all_gather(tmp, mine)
+        for a, b in zip(parts, tmp):
+            a.copy_(b)
+
+
+def torch_empty_like(t):
+    import torch
+    return torch.empty_like(t)
+
+
+def exchange_reduce(image, n_images, ncell, dims, reduce_image, divide, work=None, gather="all"):
+    """The one exchange step of the path, `image = sum(fetch.(futures))` (cic_interpolation.jl:199, :256), fused with the
+    reduce_image division: the flat partial image ((n_images+1) planes of `ncell`, weight plane last) is
+    REDUCE-SCATTERED plane by plane, so rank r receives the summed planes of pixel slice r only (half the traffic of an
+    all-reduce), divides its slice (`divide(q_slice, w_slice, n, stride, n_images, dims, reduce_image)` — on the device:
+    s2g_divide_slice_dev), and the quantity slices are gathered ("all": on every rank, like the reference's master
+    returning the map to every caller of the sharded API; "root": on rank 0 only).
+    Returns the reduced flat quantity planes (n_images * ncell, NOT transposed) or None on non-root ranks.
+    Falls back to all-reduce + whole-image division when ncell is not divisible by the world size."""
+    import torch
+    dist = _dist()
+    ws, rank = world()
+    planes = n_images + 1
+    if ws == 1 or ncell % ws != 0:
+        if ws > 1:
+            dist.all_reduce(image, op=dist.ReduceOp.SUM)
+        divide(image[:n_images * ncell], image[n_images * ncell:], ncell, ncell, n_images, dims, reduce_image)
+        return image[:n_images * ncell]
+    sl = ncell // ws
+    work = work if work is not None else {}
+    mine = work.get("mine")
+    if mine is None or mine.numel() != planes * sl:
+        mine = work["mine"] = torch.empty(planes * sl, dtype=image.dtype, device=image.device)
+    for k in range(planes):
+        _reduce_scatter_plane(mine[k * sl:(k + 1) * sl], image[k * ncell:(k + 1) * ncell])
+    divide(mine[:n_images * sl], mine[n_images * sl:], sl, sl, n_images, dims, reduce_image)
+    if gather == "root" and rank != 0:
+        for k in range(n_images):
+            dist.gather(mine[k * sl:(k + 1) * sl], None, dst=0)
+        return None
+    out = work.get("out")
+    if out is None or out.numel() != n_images * ncell:
+        out = work["out"] = torch.empty(n_images * ncell, dtype=image.dtype, device=image.device)
+    for k in range(n_images):
+        if gather == "root":
+            dist.gather(mine[k * sl:(k + 1) * sl], [out[k * ncell + i * sl:k * ncell + (i + 1) * sl] for i in range(ws)],
+                        dst=0)
+        else:
+            _all_gather_plane(out[k * ncell:(k + 1) * ncell], mine[k * sl:(k + 1) * sl])
+    return out
+
+
+def device_divide(ctx):
+    """`divide` callback of exchange_reduce for CUDA tensors: s2g_divide_slice_dev on the context's stream."""
+    def divide(q, w, n, stride, n_images, dims, reduce_image):
+        check(lib().s2g_divide_slice_dev(ctx.handle, int(dims), ptr(q.data_ptr()), ptr(w.data_ptr()), int(n),
+                                         int(stride), int(n_images), int(bool(reduce_image))))
+    return divide
+
+
+def footprint_balanced_decomposition(footprints, world_size):
+    """Contiguous particle ranges with (nearly) equal SUMS of footprint pixels instead of equal particle counts — the
+    work of a particle is its footprint (cic_shared.jl:46-52 gives the box), so clustered inputs shard evenly.
+    `domain_decomposition` (parallel/domain_decomp.jl:7-17) stays the literal, count-balanced mode.
+    Returns [(start, end)] * world_size covering [0, N)."""
+    f = np.asarray(footprints, dtype=np.float64)
+    n = f.shape[0]
+    if n == 0 or world_size <= 1:
+        return [(0, n)] + [(n, n)] * (world_size - 1)
+    c = np.cumsum(np.maximum(f, 1.0))          # every particle costs at least its set-up
+    cuts = np.searchsorted(c, c[-1] * np.arange(1, world_size) / world_size, side="left") + 1
+    cuts = np.minimum(np.maximum.accumulate(cuts), n)
+    edges = [0] + [int(x) for x in cuts] + [n]
+    return [(edges[i], edges[i + 1]) for i in range(world_size)]
+
+
 def combine_partial_images(partial: np.ndarray, finite_guard: bool = False) -> np.ndarray:
     """Host-array front end of the exchange step (used by the gloo tests and by streaming accumulation):
     sums `partial` over ranks.  finite_guard reproduces distributed_mapping/cic.jl:63-69 (NaN/Inf entries of a
@@ -58,9 +154,11 @@ def combine_partial_images(partial: np.ndarray, finite_guard: bool = False) -> n
 
 
 def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid, dimensions, calc_mean, reduce_image,
-                        return_both_maps):
+                        return_both_maps, balance="footprint"):
     """Body of sphMapping(parallel=true) on this rank's GPU.  Every rank holds the full input (like the reference's
-    master) and deposits its own contiguous slice; every rank returns the full result."""
+    master) and deposits its own contiguous slice; every rank returns the full result.
+    balance = "footprint" (default): slices of equal summed footprint (s2g_footprints + prefix sum);
+              "count": the reference's domain_decomposition (parallel/domain_decomp.jl:7-17)."""
     import torch
     from .mapping import center_particles
     ws, rank = world()
@@ -84,6 +182,21 @@ def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid
     npix = int(par.Npixels[0])
     ncell = npix * npix if dimensions == 2 else npix ** 3
     planes = nim + 1 if dimensions == 2 else 2
+    if balance == "footprint" and ws > 1 and n > 0:
+        # every rank computes the same split from the same (full) arrays: pix_index_min_max boxes of the particles as
+        # they will be deposited (positions recentred like the deposit recentres them)
+        from .mapping import center_particles as _cp
+        pc = np.array(pos, copy=True)
+        if recentre_after:
+            _cp(pc, param, ctx=ctx)
+        b = np.zeros((n, 2 * dimensions), dtype=np.int64)
+        check(lib().s2g_footprints(ctx.handle, ptr(np.ascontiguousarray(pc, dtype=want)), ptr(hs), n, code,
+                                   float(par.len2pix), npix, dimensions, ptr(b)))
+        fp = np.ones(n)
+        for d_ in range(dimensions):
+            fp *= np.maximum(b[:, 2 * d_ + 1] - b[:, 2 * d_] + 1, 0)
+        s, e = footprint_balanced_decomposition(fp, ws)[rank]
+        pos_up = np.ascontiguousarray(pos[s:e], dtype=want) if not recentre_after else pos[s:e]
     dev = torch.device("cuda", ctx.device)
     with torch.cuda.device(dev):
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
@@ -96,19 +209,20 @@ def sph_mapping_sharded(ctx, pos, hs, mm, rr, bq, ww, nim, code, param, par, kid
                                    e - s, nim, code, dbl3(shift), periodic, boxsize,
                                    dbl3(par.halfsize), float(par.len2pix), npix, kid, int(calc_mean), 0,
                                    ptr(image.data_ptr())))
-        allreduce_sum_(image)  # image = sum(fetch.(futures))
         if dimensions == 2 and return_both_maps:
+            allreduce_sum_(image)  # image = sum(fetch.(futures)); both maps go back undivided
             out = image.cpu().numpy().reshape((ncell, planes), order="F")
         else:
-            red = torch.empty(ncell * (nim if dimensions == 2 else 1), dtype=torch.float64, device=dev)
+            # reduce-scatter + per-rank division of its pixel slice + gather (exchange_reduce), then the transposition
+            nq = nim if dimensions == 2 else 1
+            flat = exchange_reduce(image, nq, ncell, dimensions, reduce_image, device_divide(ctx))
             if dimensions == 2:
-                check(lib().s2g_reduce_image_2d_dev(ctx.handle, ptr(image.data_ptr()), npix, npix, nim,
-                                                    int(bool(reduce_image)), ptr(red.data_ptr())))
+                red = torch.empty(ncell * nim, dtype=torch.float64, device=dev)
+                check(lib().s2g_reduce_image_2d_dev(ctx.handle, ptr(flat.data_ptr()), npix, npix, nim, 0,
+                                                    ptr(red.data_ptr())))   # reduce_image = 0: transposition only
                 out = red.cpu().numpy().reshape((npix, npix, nim), order="F")
             else:
-                check(lib().s2g_reduce_image_3d_dev(ctx.handle, ptr(image.data_ptr()), npix, int(bool(reduce_image)),
-                                                    ptr(red.data_ptr())))
-                out = red.cpu().numpy().reshape((npix, npix, npix), order="F")
+                out = flat.cpu().numpy().reshape((npix, npix, npix), order="F")
         torch.cuda.current_stream(dev).synchronize()
     # Q1: the reference recentres the caller's Pos before slicing
     if recentre_after:

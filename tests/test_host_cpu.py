@@ -162,6 +162,72 @@ def test_world_size_2_gloo_shard_and_reduce(s2g, oracle):
     assert np.array_equal(total, a + b)
 
 
+# ---- the reduce-scatter exchange (exchange_reduce) and footprint-balanced shards over gloo, world_size 2
+def _worker_exchange(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from oracle import oracle as orc
+    s2g = ge.load_package()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(78)
+    n = 1200
+    pos = (rng.random((n, 3)) - 0.5) * 10; hs = rng.random(n) * 0.8 + 0.01
+    hs[:300] *= 3.0                                   # clustered work: the first quarter carries most of the footprint
+    m = rng.random(n) + 0.1; rho = rng.random(n) + 0.1; w = rng.random(n) + 0.5
+    Q = np.stack([rng.random(n), rng.random(n) * 5.0], axis=1)
+    fp = np.prod(np.diff(orc.cic_mapping_2d(pos, hs, m, rho, Q, w, 6.4, 64, "WendlandC6", 2, True, True)[1]
+                         .reshape(n, 2, 2), axis=2)[..., 0] + 1, axis=1).clip(min=0)
+    s, e = s2g.distributed.footprint_balanced_decomposition(fp, world)[rank]
+    part, _ = orc.cic_mapping_2d(pos[s:e], hs[s:e], m[s:e], rho[s:e], Q[s:e], w[s:e], 6.4, 64, "WendlandC6", 2, True)
+
+    def divide(qs, ws_, nn, stride, nim, dims, red):   # CPU stand-in of s2g_divide_slice_dev (plumbing under test)
+        for k in range(nim):
+            v = qs[k * stride:k * stride + nn]
+            if red:
+                v[ws_[:nn] > 0] /= ws_[:nn][ws_[:nn] > 0]
+
+    flat = torch.from_numpy(np.ascontiguousarray(part.ravel(order="F")))
+    out_all = s2g.distributed.exchange_reduce(flat.clone(), 2, 64 * 64, 2, True, divide, gather="all")
+    out_root = s2g.distributed.exchange_reduce(flat.clone(), 2, 64 * 64, 2, True, divide, gather="root")
+    assert (out_root is None) == (rank != 0)
+    q.put((rank, s, e, float(fp[s:e].sum()), out_all.numpy().copy(), None if out_root is None else out_root.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_reduce_scatter_exchange_and_footprint_shards(s2g, oracle):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, s0, e0, f0, all0, root0), (_, s1, e1, f1, all1, root1) = res
+    assert s0 == 0 and e0 == s1 and e1 == 1200 and e0 < 600          # the heavy quarter gets the smaller slice
+    assert abs(f0 - f1) / (f0 + f1) < 0.05                            # summed footprints balanced
+    rng = np.random.default_rng(78)
+    n = 1200
+    pos = (rng.random((n, 3)) - 0.5) * 10; hs = rng.random(n) * 0.8 + 0.01
+    hs[:300] *= 3.0
+    m = rng.random(n) + 0.1; rho = rng.random(n) + 0.1; w = rng.random(n) + 0.5
+    Q = np.stack([rng.random(n), rng.random(n) * 5.0], axis=1)
+    a, _ = oracle.cic_mapping_2d(pos[:e0], hs[:e0], m[:e0], rho[:e0], Q[:e0], w[:e0], 6.4, 64, "WendlandC6", 2, True)
+    b, _ = oracle.cic_mapping_2d(pos[e0:], hs[e0:], m[e0:], rho[e0:], Q[e0:], w[e0:], 6.4, 64, "WendlandC6", 2, True)
+    tot = a + b
+    ref = np.where(tot[:, 2:3] > 0, tot[:, :2] / np.where(tot[:, 2:3] > 0, tot[:, 2:3], 1.0), tot[:, :2]).ravel(order="F")
+    for got in (all0, all1, root0):
+        assert np.array_equal(got, ref)
+    assert root1 is None
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
     timed on the oracle port, no GPU needed.  Tiny sample so that the test takes a second."""
