@@ -488,12 +488,17 @@ def run_workload(e, name, steps, warmup, main):
                 h_out2 = np.empty(ncell * 2)
             ms_e, wall_e = timed(step_e2e, max(1, min(steps, 5)), 1)
             res[kind] = max(ms_e, wall_e)
+            if world == 1:
+                stx = ctx.stats()
+                res[kind + "_phases"] = {k: round(float(stx.get(k, 0.0)), 2) for k in
+                                         ("ms_h2d", "ms_compute", "ms_epilogue", "ms_d2h", "ms_total")}
         n_in_arrays = sum(1 for a in host if a is not None)
         e2e = {"value": n_mapped / (res["pageable"] * 1e-3) / 1e6, "unit": "Mparticles/s",
                "h2d_bytes_per_step": int(sum(a.nbytes for a in host if a is not None) * world),
                "d2h_bytes_per_step": int(ncell * 8 * (2 if (healpix or stencil) else 1)),
                "ms_per_step": res["pageable"], "host_memory": "pageable (numpy = Julia Array)",
-               "pinned_ms_per_step": res.get("pinned"), "arrays": n_in_arrays}
+               "pinned_ms_per_step": res.get("pinned"), "arrays": n_in_arrays,
+               "phases_last_call": res.get("pageable_phases")}
         del host
 
     result = None

@@ -155,6 +155,166 @@ __global__ void __launch_bounds__(256) k_scatter2d(s2g_particles P, s2g_geom G, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// sub-warp particles: footprints of at most SUB*8 pixels (a few pixels across) leave most of a warp idle and pay the
+// per-particle set-up (record, four overlaps, three divisions of the normalisation) once per WARP.  Here SUB lanes
+// share a particle (32/SUB particles per warp, each with its own footprint); a lane walks the flattened footprint
+// t = sub, sub+SUB, ... (j fastest, so the lanes of a group write neighbouring pixels); the pass-A sums are reduced
+// inside the group by xor-shuffles below SUB.  Same arithmetic per pixel as warp_deposit_2d.
+// ------------------------------------------------------------------------------------------------
+template <int KID, int SUB>
+__global__ void __launch_bounds__(256) k_scatter2d_sub(s2g_particles P, s2g_geom G, const int* __restrict__ list,
+                                                       long long n_list, double* __restrict__ image,
+                                                       unsigned long long* __restrict__ counters)
+{
+    constexpr int GROUPS = 32 / SUB;
+    constexpr int CHUNK = 4 * GROUPS;
+    const int lane = threadIdx.x & 31, grp = lane / SUB, sub = lane % SUB;
+    unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
+    const long long npl = G.npix * G.npix;
+    double* __restrict__ wplane = image + npl * G.n_images;
+    const int nim = G.n_images;
+    for (;;) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_list) break;
+        for (long long t0 = base; t0 < min(base + CHUNK, n_list); t0 += GROUPS) {
+            const long long t = t0 + grp;
+            long long p = 0;
+            Rec2 r;
+            bool act = t < n_list;
+            if (act) {
+                p = list ? (long long)list[t] : t;
+                act = make_rec2(P, G, p, r);
+            }
+            int ni = 0, nj = 1, npx = 0;
+            double dx_lo = 0, dx_hi = 0, dy_lo = 0, dy_hi = 0;
+            if (act) {
+                ni = r.iMax - r.iMin + 1; nj = r.jMax - r.jMin + 1; npx = ni * nj;
+                dx_lo = overlap_1d(r.x, r.h, r.iMin); dx_hi = overlap_1d(r.x, r.h, r.iMax);
+                dy_lo = overlap_1d(r.y, r.h, r.jMin); dy_hi = overlap_1d(r.y, r.h, r.jMax);
+                if (sub == 0) { ++mapped; fpx += (unsigned long long)npx; }
+            }
+            // ---- pass A
+            double sw = 0.0, da = 0.0;
+            int cnt = 0;
+            for (int e = sub; e < npx; e += SUB) {
+                const int ir = e / nj, jc = e - ir * nj;
+                const int i = r.iMin + ir, j = r.jMin + jc;
+                const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
+                const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+                const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
+                da += dx * dy;
+                if (u <= 1.0) {
+                    sw = fma(kernel_shape<KID>(u), dx * dy, sw);
+                    ++cnt;
+                }
+            }
+#pragma unroll
+            for (int o = SUB / 2; o > 0; o >>= 1) {
+                sw += __shfl_xor_sync(0xffffffffu, sw, o);
+                da += __shfl_xor_sync(0xffffffffu, da, o);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            }
+            if (!act) continue;   // (after the shuffles: every lane of the warp takes part in them)
+            // ---- normalisation (cic_2D.jl:51-69, :187-188)
+            bool fb = false;
+            double n_distr, wpp;
+            if (sw == 0.0) {
+                fb = true;
+                n_distr = (double)ni * (double)nj;
+                wpp = (da != 0.0) ? n_distr / da : 1.0;
+                if (sub == 0) ++fallback;
+            } else {
+                n_distr = (double)cnt;
+                wpp = n_distr / sw;
+            }
+            const double kernel_norm = r.area / n_distr;
+            const double area_norm = kernel_norm * wpp * r.w * r.dz;
+            const bool poison = !isfinite(area_norm);
+            double q0 = 0.0;
+            if (!r.all_zero && nim == 1) q0 = ld_in(P.binq, p, P.in_dtype);
+            // ---- pass B
+            for (int e = sub; e < npx; e += SUB) {
+                const int ir = e / nj, jc = e - ir * nj;
+                const int i = r.iMin + ir, j = r.jMin + jc;
+                const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
+                double wk;
+                if (fb)
+                    wk = 1.0;
+                else {
+                    const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
+                    if (!(u <= 1.0)) {
+                        if (!poison) continue;
+                        wk = 0.0;
+                    } else
+                        wk = kernel_shape<KID>(u);
+                }
+                const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+                const double pw = wk * (dx * dy) * area_norm;
+                if (pw != 0.0) {
+                    const long long idx = (long long)i * G.npix + j;
+                    red_add(wplane + idx, pw);
+                    if (r.all_zero) {
+                        if (!isfinite(pw)) red_add(image + idx, 0.0 * pw);
+                    } else if (nim == 1) {
+                        red_add(image + idx, q0 * pw);
+                    } else {
+                        for (int q = 0; q < nim; ++q)
+                            red_add(image + npl * q + idx, ld_in(P.binq, (long long)nim * p + q, P.in_dtype) * pw);
+                    }
+                    ++touched;
+                }
+            }
+        }
+    }
+    touched = (unsigned long long)warp_sum_ll((long long)touched);
+    fallback = (unsigned long long)warp_sum_ll((long long)fallback);
+    mapped = (unsigned long long)warp_sum_ll((long long)mapped);
+    fpx = (unsigned long long)warp_sum_ll((long long)fpx);
+    if (lane == 0) {
+        if (touched) atomicAdd(&counters[CNT_TOUCHED], touched);
+        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
+        if (mapped) atomicAdd(&counters[CNT_MAPPED], mapped);
+        if (mapped) atomicAdd(&counters[CNT_SCATTER], mapped);
+        if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
+    }
+}
+
+template <int KID>
+static int launch_scatter2d_sub_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list,
+                                  long long n_list, double* image)
+{
+    if (n_list <= 0) return S2G_OK;
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    const long long warps_needed = std::min<long long>((n_list + 15) / 16, (long long)ctx->sm_count * 8 * 8);
+    int blocks = (int)std::max<long long>(1, (warps_needed + 7) / 8);
+    blocks = min(blocks, ctx->sm_count * 8);
+    k_scatter2d_sub<KID, 8><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters);
+    S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return S2G_OK;
+}
+
+// sub-warp launch for a list of particles whose footprints hold at most S2G_TINY_MAX_PIXELS (64) pixels
+int s2g_launch_scatter_2d_tiny(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const int* list,
+                               long long n_list, double* image)
+{
+    switch (kernel) {
+    case S2G_KERNEL_CUBIC: return launch_scatter2d_sub_k<S2G_KERNEL_CUBIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_QUINTIC: return launch_scatter2d_sub_k<S2G_KERNEL_QUINTIC>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C2: return launch_scatter2d_sub_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C4: return launch_scatter2d_sub_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C6: return launch_scatter2d_sub_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, G, list, n_list, image);
+    case S2G_KERNEL_WENDLAND_C8: return launch_scatter2d_sub_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, G, list, n_list, image);
+    }
+    s2g_set_error("unknown kernel id %d", kernel);
+    return S2G_EINVAL;
+}
+
 template <int KID>
 static int launch_scatter2d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list,
                               long long n_list, double* image)

@@ -17,6 +17,8 @@
 
 int s2g_launch_scatter_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const int* list,
                           long long n_list, double* image);
+int s2g_launch_scatter_2d_tiny(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, const int* list,
+                               long long n_list, double* image);
 
 namespace {
 
@@ -88,10 +90,11 @@ __device__ __forceinline__ bool tile_hit(const GRec& g, int ti, int tj)
     return ddx * ddx + ddy * ddy <= hh * hh;
 }
 
-// class: 0 = nothing to do, 1 = scatter, 2 = gather
+// class: 0 = nothing to do, 1 = scatter (warp per particle), 2 = gather, 3 = tiny scatter (8 lanes per particle)
+// — the footprint-size bins of the deposit (F_p = product of the pix_index_min_max ranges, cic_shared.jl:46-52)
 __global__ void __launch_bounds__(256) k_classify(s2g_particles P, s2g_geom G, long long p0, long long nb,
-                                                  long long gather_min_pixels, int force, int* __restrict__ cls,
-                                                  unsigned* __restrict__ npairs)
+                                                  long long gather_min_pixels, long long tiny_max_pixels, int force,
+                                                  int* __restrict__ cls, unsigned* __restrict__ npairs)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nb) return;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256) k_classify(s2g_particles P, s2g_geom G, l
     if (make_rec2(P, G, p0 + t, r)) {
         const long long fp = (long long)(r.iMax - r.iMin + 1) * (r.jMax - r.jMin + 1);
         const bool gather = force == S2G_STRATEGY_GATHER || (force == S2G_STRATEGY_AUTO && fp >= gather_min_pixels);
-        c = gather ? 2 : 1;
+        c = gather ? 2 : (fp <= tiny_max_pixels ? 3 : 1);
         if (gather)  // upper bound of the number of (tile, particle) pairs
             np = (unsigned)((r.iMax / TILE_H - r.iMin / TILE_H + 1) * (r.jMax / TILE_W - r.jMin / TILE_W + 1));
     }
@@ -111,14 +114,17 @@ __global__ void __launch_bounds__(256) k_classify(s2g_particles P, s2g_geom G, l
 
 // compact lists of scatter and gather particles (indices relative to the whole particle set)
 __global__ void __launch_bounds__(256) k_build_lists(const int* __restrict__ cls, const unsigned* __restrict__ pos_s,
-                                                     const unsigned* __restrict__ pos_g, long long p0, long long nb,
-                                                     int* __restrict__ list_s, int* __restrict__ list_g)
+                                                     const unsigned* __restrict__ pos_g,
+                                                     const unsigned* __restrict__ pos_t, long long p0, long long nb,
+                                                     int* __restrict__ list_s, int* __restrict__ list_g,
+                                                     int* __restrict__ list_t)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nb) return;
     const int c = cls[t];
     if (c == 1) list_s[pos_s[t]] = (int)(p0 + t);
     if (c == 2) list_g[pos_g[t]] = (int)(p0 + t);
+    if (c == 3) list_t[pos_t[t]] = (int)(p0 + t);
 }
 
 // Σ w(u)·dA over the pixel centres inside the kernel, for the pixel rectangle [ia,ib] x [ja,jb] (indices may lie
@@ -688,6 +694,7 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
     }
 
     const long long gather_min = env_ll("S2G_GATHER_MIN_PIXELS", 1024);
+    const long long tiny_max = env_ll("S2G_TINY_MAX_PIXELS", 64);   // 0: no sub-warp bin
     const long long batch_max = env_ll("S2G_BATCH_PARTICLES", 8LL << 20);
     const long long pair_cap = env_ll("S2G_PAIR_CAP", 512LL << 20);
     const int exact_norm = (int)env_ll("S2G_EXACT_NORM", 0) || ctx->exact_norm;
@@ -711,15 +718,20 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         S2G_TRY(s2g_scratch(ctx, "g_pos_g", sizeof(unsigned) * (nb + 1), &d_pg));
         S2G_TRY(s2g_scratch(ctx, "g_list_s", sizeof(int) * nb, &d_ls));
         S2G_TRY(s2g_scratch(ctx, "g_list_g", sizeof(int) * nb, &d_lg));
+        void *d_pt, *d_lt;
+        S2G_TRY(s2g_scratch(ctx, "g_pos_t", sizeof(unsigned) * (nb + 1), &d_pt));
+        S2G_TRY(s2g_scratch(ctx, "g_list_t", sizeof(int) * nb, &d_lt));
         S2G_TRY(s2g_scratch(ctx, "g_sum", sizeof(unsigned long long), &d_sum));
         const int blocks = (int)((nb + 255) / 256);
         int ph = s2g_phase_begin(ctx, PH_PREP);
         S2G_CUDA(cudaMemsetAsync((int*)d_cls + nb, 0, sizeof(int), st));
-        k_classify<<<blocks, 256, 0, st>>>(P, G, p0, nb, gather_min, ctx->strategy, (int*)d_cls, (unsigned*)d_np);
+        k_classify<<<blocks, 256, 0, st>>>(P, G, p0, nb, gather_min, tiny_max, ctx->strategy, (int*)d_cls,
+                                           (unsigned*)d_np);
         S2G_CUDA(cudaGetLastError());
 
         cub::TransformInputIterator<unsigned, IsClass, const int*> it_s((const int*)d_cls, IsClass{1});
         cub::TransformInputIterator<unsigned, IsClass, const int*> it_g((const int*)d_cls, IsClass{2});
+        cub::TransformInputIterator<unsigned, IsClass, const int*> it_t((const int*)d_cls, IsClass{3});
         cub::TransformInputIterator<unsigned long long, ToU64, const unsigned*> it_np((const unsigned*)d_np, ToU64{});
         size_t t1 = 0, t2 = 0, t3 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, t1, it_s, (unsigned*)d_ps, (int)(nb + 1), st);
@@ -732,11 +744,14 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         tb = tmp_bytes;
         S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, it_g, (unsigned*)d_pg, (int)(nb + 1), st));
         tb = tmp_bytes;
+        S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, it_t, (unsigned*)d_pt, (int)(nb + 1), st));
+        tb = tmp_bytes;
         S2G_CUDA(cub::DeviceReduce::Sum(d_tmp, tb, it_np, (unsigned long long*)d_sum, (int)nb, st));
-        unsigned h_ns = 0, h_ng = 0;
+        unsigned h_ns = 0, h_ng = 0, h_nt = 0;
         unsigned long long h_ub = 0;
         S2G_CUDA(cudaMemcpyAsync(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        S2G_CUDA(cudaMemcpyAsync(&h_nt, (unsigned*)d_pt + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         S2G_CUDA(cudaMemcpyAsync(&h_ub, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         s2g_phase_end(ctx, ph);
         ctx->launches += 4;
@@ -748,12 +763,18 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         S2G_CHECK(h_ub < 0xfff00000ull, S2G_ENOMEM,
                   "a single slice of %lld particles spans %llu image tiles: footprints too large for this image",
                   nb, h_ub);
-        const long long n_s = h_ns, n_g = h_ng;
-        k_build_lists<<<blocks, 256, 0, st>>>((const int*)d_cls, (const unsigned*)d_ps, (const unsigned*)d_pg, p0, nb,
-                                              (int*)d_ls, (int*)d_lg);
+        const long long n_s = h_ns, n_g = h_ng, n_t = h_nt;
+        k_build_lists<<<blocks, 256, 0, st>>>((const int*)d_cls, (const unsigned*)d_ps, (const unsigned*)d_pg,
+                                              (const unsigned*)d_pt, p0, nb, (int*)d_ls, (int*)d_lg, (int*)d_lt);
         S2G_CUDA(cudaGetLastError());
         ctx->launches += 1;
 
+        // ---- tiny bin (a few pixels): 8 lanes per particle
+        if (n_t > 0) {
+            ph = s2g_phase_begin(ctx, PH_DEPOSIT);
+            S2G_TRY(s2g_launch_scatter_2d_tiny(ctx, P, G, kernel, (const int*)d_lt, n_t, image));
+            s2g_phase_end(ctx, ph);
+        }
         // ---- scatter bin (small footprints)
         if (n_s > 0) {
             ph = s2g_phase_begin(ctx, PH_DEPOSIT);
