@@ -59,6 +59,7 @@ extern "C" int s2g_init(int device, s2g_ctx** out)
     for (auto& ev : ctx->ev) S2G_CUDA(cudaEventCreate(&ev));
     S2G_CUDA(cudaMalloc(&ctx->d_counters, CNT_N * sizeof(unsigned long long)));
     S2G_CUDA(cudaMallocHost(&ctx->h_counters, CNT_N * sizeof(unsigned long long)));
+    S2G_CUDA(cudaMallocHost(&ctx->h_small, 256));
     S2G_CUDA(cudaMemset(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long)));
     *out = ctx;
     return S2G_OK;
@@ -79,6 +80,7 @@ extern "C" int s2g_shutdown(s2g_ctx* ctx)
     for (auto& t : ctx->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return S2G_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <stdint.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -60,6 +61,7 @@ struct s2g_ctx {
     // device-side counters (footprint pixels, touched, fallback, mapped, pairs ...)
     unsigned long long* d_counters = nullptr;  // 16 x u64
     unsigned long long* h_counters = nullptr;  // pinned mirror
+    unsigned char* h_small = nullptr;          // 256 pinned bytes for the small device->host read-backs (s2g_readback)
     // per-phase device timers: (phase, start, stop) event pairs recorded on the stream, summed in s2g_get_stats
     struct timer { int phase; cudaEvent_t a, b; };
     std::vector<timer> timers;
@@ -74,6 +76,32 @@ struct s2g_ctx {
 int s2g_stage_wait(s2g_ctx* ctx, long long upto);
 // first slice of a sliced deposit while a staging thread runs (small, so that the deposit starts early); 0 = no limit
 long long s2g_stage_first_slice(const s2g_ctx* ctx);
+
+// Small device->host read-backs (list lengths, pair counts) through PINNED memory.  A cudaMemcpyAsync into a pageable
+// stack variable takes the driver's pageable-staging path, which serialises with the pageable host->device copies of
+// the overlapped staging thread (s2g_api.cu) — measured: ~60 ms of stalls per C2 map.  Usage: add() ... then sync().
+struct s2g_readback {
+    s2g_ctx* ctx;
+    int n = 0;
+    size_t used = 0;
+    struct { void* dst; size_t off, bytes; } item[8];
+    explicit s2g_readback(s2g_ctx* c) : ctx(c) {}
+    cudaError_t add(void* dst, const void* dev_src, size_t bytes)
+    {
+        item[n].dst = dst; item[n].off = used; item[n].bytes = bytes;
+        const cudaError_t e = cudaMemcpyAsync(ctx->h_small + used, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        used += (bytes + 7) & ~(size_t)7;
+        ++n;
+        return e;
+    }
+    cudaError_t sync()
+    {
+        const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < n; ++i) memcpy(item[i].dst, ctx->h_small + item[i].off, item[i].bytes);
+        n = 0; used = 0;
+        return e;
+    }
+};
 
 enum { PH_PREP = 0, PH_SORT = 1, PH_NORM = 2, PH_DEPOSIT = 3, PH_EPILOGUE = 4, PH_N = 5 };
 // records the start of a phase; returns a handle for s2g_phase_end

@@ -749,13 +749,14 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
         S2G_CUDA(cub::DeviceReduce::Sum(d_tmp, tb, it_np, (unsigned long long*)d_sum, (int)nb, st));
         unsigned h_ns = 0, h_ng = 0, h_nt = 0;
         unsigned long long h_ub = 0;
-        S2G_CUDA(cudaMemcpyAsync(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        S2G_CUDA(cudaMemcpyAsync(&h_nt, (unsigned*)d_pt + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        S2G_CUDA(cudaMemcpyAsync(&h_ub, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        s2g_readback rb(ctx);
+        S2G_CUDA(rb.add(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned)));
+        S2G_CUDA(rb.add(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned)));
+        S2G_CUDA(rb.add(&h_nt, (unsigned*)d_pt + nb, sizeof(unsigned)));
+        S2G_CUDA(rb.add(&h_ub, d_sum, sizeof(unsigned long long)));
         s2g_phase_end(ctx, ph);
         ctx->launches += 4;
-        S2G_CUDA(cudaStreamSynchronize(st));
+        S2G_CUDA(rb.sync());
         if ((long long)h_ub > pair_cap && nb > 1024) {  // too many (tile,particle) pairs: shrink the slice, redo it
             batch = std::max<long long>(1024, nb / 2);
             continue;
@@ -803,10 +804,9 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
                                                    (int)(n_g + 1), st));
             unsigned h_m = 0;
             unsigned long long h_rr = 0;
-            S2G_CUDA(cudaMemcpyAsync(&h_m, (unsigned*)d_off + n_g, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            S2G_CUDA(cudaMemcpyAsync(&h_rr, ctx->d_counters + CNT_PAIRS, sizeof(unsigned long long),
-                                     cudaMemcpyDeviceToHost, st));
-            S2G_CUDA(cudaStreamSynchronize(st));
+            S2G_CUDA(rb.add(&h_m, (unsigned*)d_off + n_g, sizeof(unsigned)));
+            S2G_CUDA(rb.add(&h_rr, ctx->d_counters + CNT_PAIRS, sizeof(unsigned long long)));
+            S2G_CUDA(rb.sync());
             const long long m = h_m;
             if (h_rr > 0) {  // "no pixel centre covered" particles found by pass A -> scatter kernel
                 s2g_phase_end(ctx, ph);
@@ -853,12 +853,11 @@ int s2g_launch_deposit_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& 
                 S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tbb, (const unsigned*)d_nch, (unsigned*)d_cbeg,
                                                        ntiles + 1, st));
                 unsigned h_chunks = 0;
-                S2G_CUDA(cudaMemcpyAsync(&h_chunks, (unsigned*)d_cbeg + ntiles, sizeof(unsigned),
-                                         cudaMemcpyDeviceToHost, st));
+                S2G_CUDA(rb.add(&h_chunks, (unsigned*)d_cbeg + ntiles, sizeof(unsigned)));
                 s2g_phase_end(ctx, ph);
                 ph = -1;
                 ctx->launches += 8;
-                S2G_CUDA(cudaStreamSynchronize(st));
+                S2G_CUDA(rb.sync());
                 const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
                 for (int k = 0; k < G.n_images; ++k)
                     S2G_TRY(K.gather(ctx, (const GRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,

@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
             if (threadIdx.x == 0) s_pick = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
             __syncthreads();
             p = s_pick;
-            if (p >= (long long)*n_heavy) break;
+            if (p >= (REC ? n_list_val : (long long)*n_heavy)) break;
+            t_rec = p;
             p = heavy_list[p];
+            if (REC && threadIdx.x == 0) { recs[t_rec].rmin = 1; recs[t_rec].rmax = 0; recs[t_rec].ntot = 0; }
         } else if (REC) {
             if (lane == 0) p = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
             p = __shfl_sync(0xffffffffu, p, 0);
@@ -460,8 +462,8 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
         if (REC) {
             const double an = area_norm * d.inv_aD2;
             const bool usable = !fb && q_finite && isfinite(an) && found_c && d.ring_first == d.irmin &&
-                                d.ring_last == d.irmax && d.small;
-            if (lane == 0) {
+                                d.ring_last == d.irmax && !d.full_sky;
+            if (lane == 0 && wsub == 0) {
                 if (usable) {
                     HRec r;
                     r.ux = d.ux; r.uy = d.uy; r.uz = d.uz; r.ph = d.proj_h; r.an = an; r.anq = an * q;
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(256, 2) k_healpix(s2g_particles P, HpGeom g, i
                     recs[t_rec] = r;
                 } else {
                     skip_out[p] = 0;   // the scatter launch that follows deposits (and counts) it
-                    if (fb) --fallback;
+                    if (fb && fallback) --fallback;
                 }
             }
             continue;
@@ -560,6 +562,7 @@ int set_smem_attr(s2g_ctx* ctx, size_t smem)
         S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S2G_CUDA(cudaFuncSetAttribute(k_healpix<KID, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[ctx->device & 63] = true;
     }
     return S2G_OK;
@@ -616,22 +619,26 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
     if (ctx->strategy == S2G_STRATEGY_GATHER) gather_min = std::min(gather_min, 3.0);
     const unsigned char* d_skip = nullptr;
     if (coop_on || gather_on) {
-        void *d_h, *d_g, *d_s, *d_list, *d_nh, *d_tmp;
+        void *d_h, *d_g, *d_gh, *d_s, *d_list, *d_nh, *d_tmp;
         S2G_TRY(s2g_scratch(ctx, "hp_heavy", (size_t)P.n, &d_h));
         S2G_TRY(s2g_scratch(ctx, "hp_gath", (size_t)P.n, &d_g));
+        S2G_TRY(s2g_scratch(ctx, "hp_gathh", (size_t)P.n, &d_gh));
         S2G_TRY(s2g_scratch(ctx, "hp_skip", (size_t)P.n, &d_s));
         S2G_TRY(s2g_scratch(ctx, "hp_heavy_list", sizeof(unsigned) * (size_t)P.n, &d_list));
-        S2G_TRY(s2g_scratch(ctx, "hp_heavy_n", sizeof(unsigned) * 2, &d_nh));
-        const int php = s2g_phase_begin(ctx, PH_PREP);
-        S2G_TRY(s2g_hp_classify(ctx, P, nside, calc_mean, take, coop_on ? 0.5 * (double)coop_rings * g.ang_pix : 0.0,
-                                gather_min * g.ang_pix, gather_on ? 1 : 0, (unsigned char*)d_h, (unsigned char*)d_g,
-                                (unsigned char*)d_s));
+        S2G_TRY(s2g_scratch(ctx, "hp_heavy_n", sizeof(unsigned) * 4, &d_nh));
+        const double heavy_radius = coop_on ? 0.5 * (double)coop_rings * g.ang_pix : 0.0;
+        int php = s2g_phase_begin(ctx, PH_PREP);
+        S2G_TRY(s2g_hp_classify(ctx, P, nside, calc_mean, take, heavy_radius, gather_min * g.ang_pix, gather_on ? 1 : 0,
+                                (unsigned char*)d_h, (unsigned char*)d_g, (unsigned char*)d_gh, (unsigned char*)d_s));
         cub::CountingInputIterator<unsigned> ids(0u);
         size_t tb = 0;
         cub::DeviceSelect::Flagged(nullptr, tb, ids, (const unsigned char*)d_h, (unsigned*)d_list, (unsigned*)d_nh,
                                    (int)P.n, ctx->stream);
         S2G_TRY(s2g_scratch(ctx, "hp_heavy_tmp", tb + 16, &d_tmp));
+        s2g_phase_end(ctx, php);
         if (coop_on) {
+            // heavy discs the gather cannot take (over a pole, non-finite quantity): one CTA each, scatter
+            php = s2g_phase_begin(ctx, PH_PREP);
             S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)d_h, (unsigned*)d_list,
                                                 (unsigned*)d_nh, (int)P.n, ctx->stream));
             s2g_phase_end(ctx, php);
@@ -643,20 +650,28 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
             s2g_phase_end(ctx, phc);
             S2G_CUDA(cudaGetLastError());
             ctx->launches += 3;
-        } else
-            s2g_phase_end(ctx, php);
+        }
         if (gather_on) {
-            // the gather list reuses the list buffer (the cooperative launch above is stream-ordered before it)
-            const int phl = s2g_phase_begin(ctx, PH_PREP);
-            S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)d_g, (unsigned*)d_list,
-                                                (unsigned*)d_nh + 1, (int)P.n, ctx->stream));
-            unsigned h_ng = 0;
-            S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_nh + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-            s2g_phase_end(ctx, phl);
-            S2G_CUDA(cudaStreamSynchronize(ctx->stream));
-            ctx->launches += 1;
-            S2G_TRY(s2g_hp_gather_pipeline(ctx, P, nside, KID, calc_mean, (const unsigned*)d_list, (long long)h_ng,
-                                           (unsigned char*)d_s, amap, wmap));
+            // the two gather lists reuse the list buffer (everything is stream-ordered): first the heavy discs
+            // (pass A by a whole CTA each), then the ordinary ones (pass A by a warp each)
+            for (int pass = 0; pass < 2; ++pass) {
+                const bool heavy_pass = pass == 0;
+                if (heavy_pass && !coop_on) continue;
+                const int phl = s2g_phase_begin(ctx, PH_PREP);
+                S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)(heavy_pass ? d_gh : d_g),
+                                                    (unsigned*)d_list, (unsigned*)d_nh + 1, (int)P.n, ctx->stream));
+                unsigned h_ng = 0;
+                S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_nh + 1, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+                s2g_phase_end(ctx, phl);
+                S2G_CUDA(cudaStreamSynchronize(ctx->stream));
+                ctx->launches += 1;
+                // discs above 0.2 rad need asin itself instead of its series: every heavy disc may, an ordinary one
+                // only when the heavy threshold lies above that (coarse maps)
+                const int big = heavy_pass || !coop_on || heavy_radius + 2.0 * g.ang_pix >= 0.2;
+                S2G_TRY(s2g_hp_gather_pipeline(ctx, P, nside, KID, calc_mean, (const unsigned*)d_list, (long long)h_ng,
+                                               (unsigned char*)d_s, amap, wmap, heavy_pass ? 1 : 0, big));
+            }
         }
         d_skip = (const unsigned char*)d_s;
     }
@@ -674,12 +689,21 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
 
 template <int KID>
 int launch_records_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned* list,
-                     long long n_list, HRec* recs, unsigned char* skip)
+                     long long n_list, HRec* recs, unsigned char* skip, int coop)
 {
     const HpGeom g = make_hp(nside);
     const size_t smem = 8 * (sizeof(RingBatch) + sizeof(HpStage));
     S2G_TRY(set_smem_attr<KID>(ctx, smem));
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    if (coop) {   // one CTA per (very large) disc
+        const int blocks = (int)std::min<long long>(n_list, (long long)ctx->sm_count * 2);
+        k_healpix<KID, true, true><<<max(blocks, 1), 256, smem, ctx->stream>>>(P, g, calc_mean, nullptr, nullptr, nullptr,
+                                                                               list, nullptr, false, nullptr, nullptr,
+                                                                               ctx->d_counters, n_list, recs, skip);
+        S2G_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        return S2G_OK;
+    }
     const int blocks = (int)std::min<long long>((n_list + 7) / 8, (long long)ctx->sm_count * 2);
     k_healpix<KID, false, true><<<max(blocks, 1), 256, smem, ctx->stream>>>(P, g, calc_mean, nullptr, nullptr, nullptr, list,
                                                                             nullptr, false, nullptr, nullptr,
@@ -709,15 +733,17 @@ int s2g_launch_healpix(s2g_ctx* ctx, const s2g_particles& P, long long nside, in
 }
 
 int s2g_hp_launch_records(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
-                          const unsigned* list, long long n_list, HRec* recs, unsigned char* skip)
+                          const unsigned* list, long long n_list, HRec* recs, unsigned char* skip, int coop)
 {
     switch (kernel) {
-    case S2G_KERNEL_CUBIC: return launch_records_k<S2G_KERNEL_CUBIC>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
-    case S2G_KERNEL_QUINTIC: return launch_records_k<S2G_KERNEL_QUINTIC>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
-    case S2G_KERNEL_WENDLAND_C2: return launch_records_k<S2G_KERNEL_WENDLAND_C2>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
-    case S2G_KERNEL_WENDLAND_C4: return launch_records_k<S2G_KERNEL_WENDLAND_C4>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
-    case S2G_KERNEL_WENDLAND_C6: return launch_records_k<S2G_KERNEL_WENDLAND_C6>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
-    case S2G_KERNEL_WENDLAND_C8: return launch_records_k<S2G_KERNEL_WENDLAND_C8>(ctx, P, nside, calc_mean, list, n_list, recs, skip);
+#define HPR_CASE(K) case K: return launch_records_k<K>(ctx, P, nside, calc_mean, list, n_list, recs, skip, coop);
+        HPR_CASE(S2G_KERNEL_CUBIC)
+        HPR_CASE(S2G_KERNEL_QUINTIC)
+        HPR_CASE(S2G_KERNEL_WENDLAND_C2)
+        HPR_CASE(S2G_KERNEL_WENDLAND_C4)
+        HPR_CASE(S2G_KERNEL_WENDLAND_C6)
+        HPR_CASE(S2G_KERNEL_WENDLAND_C8)
+#undef HPR_CASE
     }
     s2g_set_error("unknown kernel id %d", kernel);
     return S2G_EINVAL;

@@ -285,8 +285,9 @@ static_assert(sizeof(HRec) == 64, "HRec is one 64-byte line");
 
 int s2g_hp_classify(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned char* take,
                     double heavy_radius, double gather_radius, int gather_on, unsigned char* heavy, unsigned char* gath,
-                    unsigned char* skip);
+                    unsigned char* gath_heavy, unsigned char* skip);
 int s2g_hp_launch_records(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
-                          const unsigned* list, long long n_list, HRec* recs, unsigned char* skip);
+                          const unsigned* list, long long n_list, HRec* recs, unsigned char* skip, int coop);
 int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
-                           const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap);
+                           const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap,
+                           int coop_records, int big);

@@ -48,7 +48,7 @@ struct __align__(16) HRecS {
     double php;          // proj_h / ang_pix
     double an, anq;      // area_norm / (ang_pix Dx)^2  and the same times the quantity
     int rmin, rmax;      // disc rings
-    int pad0, pad1;
+    int big, pad1;       // big: proj_h + 2 ang_pix >= 0.2 rad -> asin itself, not its series
 };
 
 // asin(x)/x = 1 + x^2/6 + 3x^4/40 + ... written in c2 = (2x)^2 (the squared chord): G(c2) = sum kG[i] c2^i
@@ -62,12 +62,15 @@ __constant__ double kG[8] = {1.0,
                              135135.0 / 9676800.0 / 16384.0};
 
 // ---- classification: which path deposits particle p
-//   skip[p] = 1  the ordinary scatter launch must NOT take it (heavy -> cooperative launch, gather -> this file)
-//   heavy[p], gath[p]: the two lists
+//   heavy[p]      very large disc the gather cannot take (over a pole, ...) -> cooperative scatter launch
+//   gath[p]       ordinary disc for the tile-gather (pass A by a warp)
+//   gath_heavy[p] very large disc for the tile-gather (pass A by a whole CTA)
+//   skip[p] = 1   the ordinary scatter launch must NOT take it (any of the three above)
 __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, int calc_mean,
                                                      const unsigned char* __restrict__ take, double heavy_radius,
                                                      double gather_radius, int gather_on,
                                                      unsigned char* __restrict__ heavy, unsigned char* __restrict__ gath,
+                                                     unsigned char* __restrict__ gath_heavy,
                                                      unsigned char* __restrict__ skip)
 {
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -76,24 +79,27 @@ __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, 
     const double dx = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     const double hs = ld_in(P.hsml, p, P.in_dtype);
     const double q = ld_in(P.binq, p, P.in_dtype);
-    unsigned char h = 0, ga = 0;
+    unsigned char h = 0, ga = 0, gh = 0;
     const bool alive = (!take || take[p]) && (calc_mean || q != 0.0) && (dx >= hs);
     if (alive) {
         // asin(hs/dx) >= r  <=>  hs >= dx*sin(r)  (r < pi/2)
         h = (heavy_radius > 0.0 && hs >= dx * sin(heavy_radius)) ? 1 : 0;
-        if (gather_on && !h) {
+        if (gather_on) {
             const double ph = asin(__ddiv_rn(hs, dx));
             const double theta = acos(__ddiv_rn(z, dx));
             const double m = 2.0 * g.ang_pix;
             const double an_probe = ld_in(P.m, p, P.in_dtype) / ld_in(P.rho, p, P.in_dtype) * ld_in(P.w, p, P.in_dtype);
-            ga = (ph >= gather_radius && ph + m < 0.2 && theta - ph > m && theta + ph < kPi - m && isfinite(q) &&
-                  isfinite(an_probe) && an_probe != 0.0)
-                     ? 1 : 0;
+            const bool ok = ph >= gather_radius && ph < 1.5 && theta - ph > m && theta + ph < kPi - m && isfinite(q) &&
+                            isfinite(an_probe) && an_probe != 0.0;
+            if (ok) {
+                if (h) { gh = 1; h = 0; } else ga = 1;
+            }
         }
     }
     heavy[p] = h;
     gath[p] = ga;
-    skip[p] = (h || ga) ? 1 : 0;
+    gath_heavy[p] = gh;
+    skip[p] = (h || ga || gh) ? 1 : 0;
 }
 
 // ---- tile table of a resolution
@@ -230,8 +236,8 @@ __global__ void __launch_bounds__(256) k_hpg_tile_chunks(const unsigned* __restr
 }
 
 // ---- pass B
-template <int KID>
-__global__ void __launch_bounds__(HPG_THREADS, HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
+template <int KID, bool BIG>
+__global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
                                                                      const unsigned* __restrict__ vals,
                                                                      const unsigned* __restrict__ tile_beg,
                                                                      const unsigned* __restrict__ tile_end,
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(HPG_THREADS, HPG_CTAS) k_hp_gather(const HRec*
                 s.php = r.ph * inv_ang;
                 s.an = r.an; s.anq = r.anq;
                 s.rmin = r.rmin; s.rmax = r.rmax;
-                s.pad0 = 0; s.pad1 = 0;
+                s.big = (r.ph + 2.0 * g.ang_pix < 0.2) ? 0 : 1; s.pad1 = 0;
                 s_rec[t] = s;
             }
             __syncthreads();
@@ -339,15 +345,21 @@ __global__ void __launch_bounds__(HPG_THREADS, HPG_CTAS) k_hp_gather(const HRec*
                 for (int m = 0; m < HPG_PPT; ++m) {
                     if (!__any_sync(0xffffffffu, in[m])) continue;   // this 16-pixel group of both rings is outside
                     const double y = hp_rsqrt(c2[m]);
-                    const double sqh = (c2[m] * y) * hinv;            // chord / proj_h
-                    double G = fma(kG[7], c2[m], kG[6]);
-                    G = fma(G, c2[m], kG[5]);
-                    G = fma(G, c2[m], kG[4]);
-                    G = fma(G, c2[m], kG[3]);
-                    G = fma(G, c2[m], kG[2]);
-                    G = fma(G, c2[m], kG[1]);
-                    G = fma(G, c2[m], kG[0]);
-                    const double t = fma(-sqh, G, 1.0);               // 1 - u,  u = dx / proj_h
+                    double t;                                         // 1 - u,  u = dx / proj_h
+                    if (BIG && r.big) {                               // (warp-uniform) dx = 2 asin(chord / 2)
+                        const double hc = 0.5 * (c2[m] * y);
+                        t = fma(-2.0 * asin(hc < 1.0 ? hc : 1.0), hinv, 1.0);
+                    } else {
+                        const double sqh = (c2[m] * y) * hinv;        // chord / proj_h
+                        double G = fma(kG[7], c2[m], kG[6]);
+                        G = fma(G, c2[m], kG[5]);
+                        G = fma(G, c2[m], kG[4]);
+                        G = fma(G, c2[m], kG[3]);
+                        G = fma(G, c2[m], kG[2]);
+                        G = fma(G, c2[m], kG[1]);
+                        G = fma(G, c2[m], kG[0]);
+                        t = fma(-sqh, G, 1.0);
+                    }
                     // contributing_area (pixel_weights.jl:6-8): min(ang, |proj_h - (dx - ang/2)|)/ang = min(1, t php + 1/2)
                     const double ap = fma(t, php, 0.5);
                     const double a1 = ap < 1.0 ? ap : 1.0;
@@ -382,12 +394,17 @@ long long env_ll(const char* name, long long dflt)
 
 template <int KID>
 int launch_gather_k(s2g_ctx* ctx, const HRec* recs, const unsigned* vals, const unsigned* tbeg, const unsigned* tend,
-                    const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks, double* amap, double* wmap)
+                    const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks, double* amap, double* wmap,
+                    int big)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = (int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * HPG_CTAS);
-    k_hp_gather<KID><<<std::max(blocks, 1), HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T, chunks, amap,
-                                                                          wmap, ctx->d_counters);
+    const int blocks = (int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * (big ? 2 : HPG_CTAS));
+    if (big)
+        k_hp_gather<KID, true><<<std::max(blocks, 1), HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T,
+                                                                                    chunks, amap, wmap, ctx->d_counters);
+    else
+        k_hp_gather<KID, false><<<std::max(blocks, 1), HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T,
+                                                                                     chunks, amap, wmap, ctx->d_counters);
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
 }
@@ -425,11 +442,11 @@ static int hp_tiles(s2g_ctx* ctx, long long nside, HpTiles& T)
 
 int s2g_hp_classify(s2g_ctx* ctx, const s2g_particles& P, long long nside, int calc_mean, const unsigned char* take,
                     double heavy_radius, double gather_radius, int gather_on, unsigned char* heavy, unsigned char* gath,
-                    unsigned char* skip)
+                    unsigned char* gath_heavy, unsigned char* skip)
 {
     const HpGeom g = make_hp(nside);
     k_hp_classify<<<(int)((P.n + 255) / 256), 256, 0, ctx->stream>>>(P, g, calc_mean, take, heavy_radius, gather_radius,
-                                                                     gather_on, heavy, gath, skip);
+                                                                     gather_on, heavy, gath, gath_heavy, skip);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return S2G_OK;
@@ -439,7 +456,8 @@ int s2g_hp_classify(s2g_ctx* ctx, const s2g_particles& P, long long nside, int c
 // (s2g_hp_launch_records), pairs, sort, pass B.  Particles that pass A hands back (fallback branch, non-finite
 // normalisation) get skip[p] = 0 there and are deposited by the scatter launch that FOLLOWS this call.
 int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
-                           const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap)
+                           const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap,
+                           int coop_records, int big)
 {
     if (n_list <= 0) return S2G_OK;
     const HpGeom g = make_hp(nside);
@@ -456,7 +474,8 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
         S2G_TRY(s2g_scratch(ctx, "hpg_np", sizeof(unsigned) * (nb + 1), &d_np));
         S2G_TRY(s2g_scratch(ctx, "hpg_off", sizeof(unsigned) * (nb + 1), &d_off));
         int ph = s2g_phase_begin(ctx, PH_NORM);
-        S2G_TRY(s2g_hp_launch_records(ctx, P, nside, kernel, calc_mean, list + p0, nb, (HRec*)d_recs, skip));
+        S2G_TRY(s2g_hp_launch_records(ctx, P, nside, kernel, calc_mean, list + p0, nb, (HRec*)d_recs, skip,
+                                      coop_records));
         s2g_phase_end(ctx, ph);
         ph = s2g_phase_begin(ctx, PH_SORT);
         S2G_CUDA(cudaMemsetAsync((unsigned*)d_np + nb, 0, sizeof(unsigned), st));
@@ -527,7 +546,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             int rc = S2G_EINVAL;
             switch (kernel) {
 #define HPG_CASE(K) case K: rc = launch_gather_k<K>(ctx, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg, \
-                                                    (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap); break;
+                                                    (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big); break;
                 HPG_CASE(S2G_KERNEL_CUBIC)
                 HPG_CASE(S2G_KERNEL_QUINTIC)
                 HPG_CASE(S2G_KERNEL_WENDLAND_C2)
