@@ -114,14 +114,71 @@ __device__ __forceinline__ long long ring_len(const HpGeom& g, long long ring)
     return ring < g.nside ? 4 * ring : (ring <= 3 * g.nside ? g.nl4 : 4 * (g.nl4 - ring));
 }
 
+// ---- records without a ring walk: everything of main.jl:143-193 that does not need the pixel list.  `an` holds the
+// UN-normalised area·w·dz/(ang_pix Δx)² until k_hp_normalise divides it by Σ wk·A' (pass A as a tile-gather, below):
+// area_norm = kernel_norm·wpp·w·dz = (area/N)(N/Σ)·w·dz, N cancels (main.jl:32-33, pixel_weights.jl:119-137).
+__global__ void __launch_bounds__(256) k_hp_records(s2g_particles P, HpGeom g, const unsigned* __restrict__ list,
+                                                    long long n_list, HRec* __restrict__ recs)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_list) return;
+    const long long p = list[t];
+    Disc d;
+    d.px = ld_pos(P, p, 0); d.py = ld_pos(P, p, 1); d.pz = ld_pos(P, p, 2);
+    const double hs = ld_in(P.hsml, p, P.in_dtype);
+    d.Dx = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.px, d.px), __dmul_rn(d.py, d.py)), __dmul_rn(d.pz, d.pz)));
+    d.proj_h = asin(__ddiv_rn(hs, d.Dx));
+    d.hinv = __ddiv_rn(1.0, d.proj_h);
+    make_disc(g, d);
+    HRec r;
+    r.ux = d.px / d.Dx; r.uy = d.py / d.Dx; r.uz = d.pz / d.Dx;
+    r.ph = d.proj_h;
+    // particle_area_and_depth (main.jl:56-63) and :193
+    double dz = __dmul_rn(2.0, hs);
+    const double area = __ddiv_rn(__ddiv_rn(ld_in(P.m, p, P.in_dtype), ld_in(P.rho, p, P.in_dtype)), dz);
+    const double aD = __dmul_rn(g.ang_pix, d.Dx);
+    dz = __ddiv_rn(dz, __dmul_rn(aD, aD));
+    // pix_weight = area_norm·wk·A with A = A'/(ang_pix Δx)² (pixel_weights.jl:53) and area_norm = area·w·dz/Σ(wk·A):
+    // the two (ang_pix Δx)² cancel, pix_weight = (area·w·dz / Σ wk·A')·wk·A'
+    r.an = area * ld_in(P.w, p, P.in_dtype) * dz;
+    r.anq = ld_in(P.binq, p, P.in_dtype);          // the quantity; becomes an*q in k_hp_normalise
+    const bool ok = !d.full_sky && d.ring_first == d.irmin && d.ring_last == d.irmax && d.irmin <= d.irmax;
+    r.rmin = ok ? (int)d.irmin : 1;
+    r.rmax = ok ? (int)d.irmax : 0;
+    r.ntot = 0;
+    r.pad = (int)p;
+    recs[t] = r;
+}
+
+// after pass A: an := an / Σ, anq := an·q.  A record whose Σ is zero (`distr_weight == 0` branch, pixel_weights.jl:121)
+// or not finite, or whose centre pixel is not in its own disc walk (ntot < 0, set by k_hp_pairs), is dropped here and
+// handed back to the scatter walk through skip[p] = 0.
+__global__ void __launch_bounds__(256) k_hp_normalise(HRec* __restrict__ recs, const double* __restrict__ S, long long n,
+                                                      unsigned char* __restrict__ skip)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    HRec r = recs[t];
+    if (r.rmin > r.rmax) { skip[r.pad] = 0; return; }
+    const double sw = S[t];
+    const double an = r.an / sw;
+    if (!(sw > 0.0) || !isfinite(an) || r.ntot < 0) {
+        recs[t].rmin = 1; recs[t].rmax = 0; recs[t].ntot = 0;
+        skip[r.pad] = 0;
+        return;
+    }
+    recs[t].an = an;
+    recs[t].anq = an * r.anq;
+}
+
 // ---- (tile, record) pairs.  One warp per record; half-warps take alternate bands, lanes are the rings of a band.
 // The sector range of a ring is that of its query_disc pixel run (ring_run: the reference's own list), the band's
 // range the union over its rings, expressed relative to the sector holding the disc centre (the runs are intervals
 // around the particle's azimuth, possibly wrapping).
 template <bool WRITE>
-__global__ void __launch_bounds__(256) k_hp_pairs(const HRec* __restrict__ recs, long long n_rec, HpGeom g, HpTiles T,
+__global__ void __launch_bounds__(256) k_hp_pairs(HRec* __restrict__ recs, long long n_rec, HpGeom g, HpTiles T,
                                                   const unsigned* __restrict__ off, unsigned* __restrict__ npairs,
-                                                  unsigned* __restrict__ keys, unsigned* __restrict__ vals)
+                                                  unsigned* __restrict__ keys, unsigned* __restrict__ vals, int fill_ntot)
 {
     const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
     const long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -141,6 +198,8 @@ __global__ void __launch_bounds__(256) k_hp_pairs(const HRec* __restrict__ recs,
     const int b0 = (r.rmin - 1) / HPG_BR, b1 = (r.rmax - 1) / HPG_BR;
     unsigned count = 0;
     unsigned o = WRITE ? off[t] : 0u;
+    long long ntot = 0;        // Σ run lengths = length of the reference's pixel list (when the centre pixel is in it)
+    bool found_c = false;
     for (int bb = b0; bb <= b1; bb += 2) {
         const int band = bb + half;
         const long long ring = (long long)band * HPG_BR + 1 + l16;
@@ -154,6 +213,15 @@ __global__ void __launch_bounds__(256) k_hp_pairs(const HRec* __restrict__ recs,
             bool sh;
             hp_ring_info(g, ring, sp, nr, sh);
             ring_run(g, d, ring, nr, sh, j0, cnt);
+            if (!WRITE && fill_ntot) {
+                ntot += cnt;
+                const long long jc_ = d.cpix - sp;   // the centre pixel, if it lies in this ring
+                if (jc_ >= 0 && jc_ < nr && cnt > 0) {
+                    long long rel = jc_ - j0;
+                    if (rel < 0) rel += nr;
+                    found_c = found_c || rel < cnt;
+                }
+            }
             if (cnt > 0) {
                 // unwrapped sector interval of the run: pixels j0 .. j0+cnt-1 (j may exceed nr), sector = floor(j ns / nr)
                 const int k_lo = (int)((j0 * ns) / nr);
@@ -192,6 +260,13 @@ __global__ void __launch_bounds__(256) k_hp_pairs(const HRec* __restrict__ recs,
             o += (unsigned)(nsec + n_other);
         } else
             count += (unsigned)(nsec + n_other);
+    }
+    if (!WRITE && fill_ntot) {
+        ntot = warp_sum_ll(ntot);
+        found_c = __any_sync(0xffffffffu, found_c);
+        // push! + unique! (constributing_pixels.jl:16-19): a centre pixel outside its own disc walk would be one more
+        // list entry, which the gather has no place for -> negative count = "hand this particle to the scatter walk"
+        if (lane == 0) recs[t].ntot = found_c ? (int)ntot : -1;
     }
     if (!WRITE && lane == 0) npairs[t] = count;
 }
@@ -236,7 +311,10 @@ __global__ void __launch_bounds__(256) k_hpg_tile_chunks(const unsigned* __restr
 }
 
 // ---- pass B
-template <int KID, bool BIG>
+// PASSA = true: calculate_weights (pixel_weights.jl:87-140) in the same tile form — per (tile, record) pair the CTA
+// sums wk·A' over the tile's pixels (warp shuffle, then shared-memory atomics across the 8 warps) and adds the pair's
+// partial sum to Ssum[record].  No pixel-centre trig per (pixel, particle), perfect load balance for huge discs.
+template <int KID, bool BIG, bool PASSA>
 __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
                                                                      const unsigned* __restrict__ vals,
                                                                      const unsigned* __restrict__ tile_beg,
@@ -244,9 +322,11 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                                                                      const unsigned* __restrict__ chunk_begin,
                                                                      HpGeom g, HpTiles T, unsigned total_chunks,
                                                                      double* __restrict__ amap, double* __restrict__ wmap,
-                                                                     unsigned long long* __restrict__ counters)
+                                                                     unsigned long long* __restrict__ counters,
+                                                                     double* __restrict__ Ssum)
 {
     __shared__ HRecS s_rec[HPG_BATCH];
+    __shared__ double s_part[PASSA ? HPG_BATCH : 1];
     __shared__ unsigned s_work[4];
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int rt = tid >> 4, l16 = tid & 15;   // ring of the tile, lane within the ring
@@ -322,6 +402,7 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                 s.rmin = r.rmin; s.rmax = r.rmax;
                 s.big = (r.ph + 2.0 * g.ang_pix < 0.2) ? 0 : 1; s.pad1 = 0;
                 s_rec[t] = s;
+                if (PASSA) s_part[t] = 0.0;
             }
             __syncthreads();
             for (int e = 0; e < nb; ++e) {
@@ -341,6 +422,7 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                     in[m] = c2[m] < c2max;
                 }
                 const double hinv = r.hinv, php = r.php, an = r.an, anq = r.anq;
+                double part = 0.0;
 #pragma unroll
                 for (int m = 0; m < HPG_PPT; ++m) {
                     if (!__any_sync(0xffffffffu, in[m])) continue;   // this 16-pixel group of both rings is outside
@@ -365,13 +447,26 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                     const double a1 = ap < 1.0 ? ap : 1.0;
                     const double wk = hp_shape_t<KID>(t) * a1;
                     const double wka = in[m] ? wk : 0.0;
-                    acc_w[m] = fma(wka, an, acc_w[m]);
-                    acc_q[m] = fma(wka, anq, acc_q[m]);
+                    if (PASSA)
+                        part += wka;
+                    else {
+                        acc_w[m] = fma(wka, an, acc_w[m]);
+                        acc_q[m] = fma(wka, anq, acc_q[m]);
+                    }
                 }
+                if (PASSA) {
+                    part = warp_sum(part);
+                    if (lane == 0 && part != 0.0) atomicAdd(&s_part[e], part);
+                }
+            }
+            if (PASSA) {
+                __syncthreads();
+                for (int t = tid; t < nb; t += HPG_THREADS)
+                    if (s_part[t] != 0.0) atomicAdd(&Ssum[vals[b + t]], s_part[t]);
             }
         }
         // one flush per work item; lanes 0..15 of a ring write 16 consecutive pixels per group
-        if (ring_ok) {
+        if (!PASSA && ring_ok) {
 #pragma unroll
             for (int m = 0; m < HPG_PPT; ++m) {
                 const long long j = jb + l16 + 16 * m;
@@ -395,18 +490,35 @@ long long env_ll(const char* name, long long dflt)
 template <int KID>
 int launch_gather_k(s2g_ctx* ctx, const HRec* recs, const unsigned* vals, const unsigned* tbeg, const unsigned* tend,
                     const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks, double* amap, double* wmap,
-                    int big)
+                    int big, double* Ssum)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = (int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * (big ? 2 : HPG_CTAS));
-    if (big)
-        k_hp_gather<KID, true><<<std::max(blocks, 1), HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T,
-                                                                                    chunks, amap, wmap, ctx->d_counters);
-    else
-        k_hp_gather<KID, false><<<std::max(blocks, 1), HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T,
-                                                                                     chunks, amap, wmap, ctx->d_counters);
+    const int blocks = std::max((int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * (big ? 2 : HPG_CTAS)), 1);
+#define HPG_LAUNCH(B, A) k_hp_gather<KID, B, A><<<blocks, HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T, \
+                                                                                         chunks, amap, wmap, ctx->d_counters, Ssum)
+    if (Ssum) { if (big) HPG_LAUNCH(true, true); else HPG_LAUNCH(false, true); }
+    else      { if (big) HPG_LAUNCH(true, false); else HPG_LAUNCH(false, false); }
+#undef HPG_LAUNCH
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
+}
+
+int launch_gather(s2g_ctx* ctx, int kernel, const HRec* recs, const unsigned* vals, const unsigned* tbeg,
+                  const unsigned* tend, const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks,
+                  double* amap, double* wmap, int big, double* Ssum)
+{
+    switch (kernel) {
+#define HPG_CASE(K) case K: return launch_gather_k<K>(ctx, recs, vals, tbeg, tend, cbeg, g, T, chunks, amap, wmap, big, Ssum);
+        HPG_CASE(S2G_KERNEL_CUBIC)
+        HPG_CASE(S2G_KERNEL_QUINTIC)
+        HPG_CASE(S2G_KERNEL_WENDLAND_C2)
+        HPG_CASE(S2G_KERNEL_WENDLAND_C4)
+        HPG_CASE(S2G_KERNEL_WENDLAND_C6)
+        HPG_CASE(S2G_KERNEL_WENDLAND_C8)
+#undef HPG_CASE
+    }
+    s2g_set_error("unknown kernel id %d", kernel);
+    return S2G_EINVAL;
 }
 
 }  // namespace
@@ -467,20 +579,32 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
     const long long pair_cap = env_ll("S2G_PAIR_CAP", 512LL << 20);
     cudaStream_t st = ctx->stream;
     long long p0 = 0, batch = std::min(batch_max, n_list);
+    // pass A: "gather" (default) = the tile form above, no ring walk at all; "walk" (S2G_HP_PASSA=walk) = the ring walk
+    // of s2g_healpix.cu in record mode (one warp, or one CTA for a heavy disc, per particle)
+    const char* e_pa = getenv("S2G_HP_PASSA");
+    const bool passa_gather = !(e_pa && e_pa[0] == 'w');
     while (p0 < n_list) {
         const long long nb = std::min(batch, n_list - p0);
-        void *d_recs, *d_np, *d_off, *d_tmp;
+        void *d_recs, *d_np, *d_off, *d_tmp, *d_S = nullptr;
         S2G_TRY(s2g_scratch(ctx, "hpg_recs", sizeof(HRec) * nb, &d_recs));
         S2G_TRY(s2g_scratch(ctx, "hpg_np", sizeof(unsigned) * (nb + 1), &d_np));
         S2G_TRY(s2g_scratch(ctx, "hpg_off", sizeof(unsigned) * (nb + 1), &d_off));
         int ph = s2g_phase_begin(ctx, PH_NORM);
-        S2G_TRY(s2g_hp_launch_records(ctx, P, nside, kernel, calc_mean, list + p0, nb, (HRec*)d_recs, skip,
-                                      coop_records));
+        if (passa_gather) {
+            S2G_TRY(s2g_scratch(ctx, "hpg_S", sizeof(double) * nb, &d_S));
+            S2G_CUDA(cudaMemsetAsync(d_S, 0, sizeof(double) * nb, st));
+            k_hp_records<<<(int)((nb + 255) / 256), 256, 0, st>>>(P, g, list + p0, nb, (HRec*)d_recs);
+            S2G_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+        } else
+            S2G_TRY(s2g_hp_launch_records(ctx, P, nside, kernel, calc_mean, list + p0, nb, (HRec*)d_recs, skip,
+                                          coop_records));
         s2g_phase_end(ctx, ph);
         ph = s2g_phase_begin(ctx, PH_SORT);
         S2G_CUDA(cudaMemsetAsync((unsigned*)d_np + nb, 0, sizeof(unsigned), st));
         const int wblocks = (int)((nb * 32 + 255) / 256);
-        k_hp_pairs<false><<<wblocks, 256, 0, st>>>((const HRec*)d_recs, nb, g, T, nullptr, (unsigned*)d_np, nullptr, nullptr);
+        k_hp_pairs<false><<<wblocks, 256, 0, st>>>((HRec*)d_recs, nb, g, T, nullptr, (unsigned*)d_np, nullptr, nullptr,
+                                                   passa_gather ? 1 : 0);
         S2G_CUDA(cudaGetLastError());
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, (const unsigned*)d_np, (unsigned*)d_off, (int)(nb + 1), st);
@@ -498,8 +622,10 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             batch = std::max<long long>(1024, nb / 2);
             continue;
         }
-        k_hpg_count<<<(int)((nb + 255) / 256), 256, 0, st>>>((const HRec*)d_recs, nb, ctx->d_counters);
-        S2G_CUDA(cudaGetLastError());
+        if (!passa_gather) {
+            k_hpg_count<<<(int)((nb + 255) / 256), 256, 0, st>>>((const HRec*)d_recs, nb, ctx->d_counters);
+            S2G_CUDA(cudaGetLastError());
+        }
         if (m > 0) {
             void *d_keys, *d_vals, *d_keys2, *d_vals2, *d_tend, *d_tbeg, *d_nch, *d_cbeg;
             const int nt = T.ntiles;
@@ -511,8 +637,8 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             S2G_TRY(s2g_scratch(ctx, "hpg_tbeg", sizeof(unsigned) * (nt + 1), &d_tbeg));
             S2G_TRY(s2g_scratch(ctx, "hpg_nch", sizeof(unsigned) * (nt + 1), &d_nch));
             S2G_TRY(s2g_scratch(ctx, "hpg_cbeg", sizeof(unsigned) * (nt + 1), &d_cbeg));
-            k_hp_pairs<true><<<wblocks, 256, 0, st>>>((const HRec*)d_recs, nb, g, T, (const unsigned*)d_off, nullptr,
-                                                      (unsigned*)d_keys, (unsigned*)d_vals);
+            k_hp_pairs<true><<<wblocks, 256, 0, st>>>((HRec*)d_recs, nb, g, T, (const unsigned*)d_off, nullptr,
+                                                      (unsigned*)d_keys, (unsigned*)d_vals, 0);
             S2G_CUDA(cudaGetLastError());
             int bits = 1;
             while ((1 << bits) < nt) ++bits;
@@ -542,24 +668,32 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             ph = -1;
             ctx->launches += 7;
             S2G_CUDA(cudaStreamSynchronize(st));
-            const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
-            int rc = S2G_EINVAL;
-            switch (kernel) {
-#define HPG_CASE(K) case K: rc = launch_gather_k<K>(ctx, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg, \
-                                                    (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big); break;
-                HPG_CASE(S2G_KERNEL_CUBIC)
-                HPG_CASE(S2G_KERNEL_QUINTIC)
-                HPG_CASE(S2G_KERNEL_WENDLAND_C2)
-                HPG_CASE(S2G_KERNEL_WENDLAND_C4)
-                HPG_CASE(S2G_KERNEL_WENDLAND_C6)
-                HPG_CASE(S2G_KERNEL_WENDLAND_C8)
-#undef HPG_CASE
-            default: s2g_set_error("unknown kernel id %d", kernel);
+            if (passa_gather) {
+                const int pha = s2g_phase_begin(ctx, PH_NORM);
+                int rca = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
+                                        (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
+                                        (double*)d_S);
+                if (rca == S2G_OK) {
+                    k_hp_normalise<<<(int)((nb + 255) / 256), 256, 0, st>>>((HRec*)d_recs, (const double*)d_S, nb, skip);
+                    k_hpg_count<<<(int)((nb + 255) / 256), 256, 0, st>>>((const HRec*)d_recs, nb, ctx->d_counters);
+                    if (cudaGetLastError() != cudaSuccess) rca = S2G_ECUDA;
+                }
+                s2g_phase_end(ctx, pha);
+                S2G_TRY(rca);
+                ctx->launches += 3;
             }
+            const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
+            const int rc = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
+                                         (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
+                                         nullptr);
             s2g_phase_end(ctx, phg);
             S2G_TRY(rc);
             ctx->launches += 1;
             ctx->host_pairs += m;
+        }
+        else if (passa_gather) {   // no pair at all: every record of the slice goes back to the scatter walk
+            k_hp_normalise<<<(int)((nb + 255) / 256), 256, 0, st>>>((HRec*)d_recs, (const double*)d_S, nb, skip);
+            S2G_CUDA(cudaGetLastError());
         }
         if (ph >= 0) s2g_phase_end(ctx, ph);
         p0 += nb;

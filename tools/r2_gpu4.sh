@@ -1,16 +1,16 @@
 #!/bin/bash
-# round 2, GPU call 4: heavy discs through the gather, launch list of c4s, C2 e2e with pinned read-backs, full C4
+# round 2, GPU call 5: heavy discs through the gather, launch list of c4s, C2 e2e with pinned read-backs, full C4
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity_3d_healpix.py tests/test_device_group.py tests/test_golden_vectors.py -q -m gpu -x -k "healpix or golden" > gpurun_out/r2d_hp_tests.log 2>&1
-echo "rc=$?" >> gpurun_out/r2d_hp_tests.log; tail -n 3 gpurun_out/r2d_hp_tests.log
+timeout 900 python -m pytest tests/test_gpu_parity_3d_healpix.py tests/test_device_group.py tests/test_golden_vectors.py -q -m gpu -x -k "healpix or golden" > gpurun_out/r2e_hp_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2e_hp_tests.log; tail -n 3 gpurun_out/r2e_hp_tests.log
 B="python bench.py --extra none --no-parity --no-cpu-baseline"
-timeout 600 $B --workload c4s --steps 2 --warmup 1 --no-e2e > gpurun_out/r2d_c4s.json 2> gpurun_out/r2d_c4s.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2d_launches_c4s.csv $B --workload c4s --steps 1 --warmup 0 --no-e2e > gpurun_out/r2d_launches_c4s.log 2>&1
-timeout 900 $B --workload c2 --steps 3 --warmup 2 > gpurun_out/r2d_c2.json 2> gpurun_out/r2d_c2.err
-timeout 1200 $B --workload c4 --steps 1 --warmup 1 --no-e2e > gpurun_out/r2d_c4.json 2> gpurun_out/r2d_c4.err
+timeout 600 $B --workload c4s --steps 2 --warmup 1 --no-e2e > gpurun_out/r2e_c4s.json 2> gpurun_out/r2e_c4s.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2e_launches_c4s.csv $B --workload c4s --steps 1 --warmup 0 --no-e2e > gpurun_out/r2e_launches_c4s.log 2>&1
+timeout 900 $B --workload c2 --steps 3 --warmup 2 > gpurun_out/r2e_c2.json 2> gpurun_out/r2e_c2.err
+timeout 1200 $B --workload c4 --steps 1 --warmup 1 --no-e2e > gpurun_out/r2e_c4.json 2> gpurun_out/r2e_c4.err
 python - <<'PY'
 import json,glob,csv,collections
-for f in sorted(glob.glob("gpurun_out/r2d_*.json")):
+for f in sorted(glob.glob("gpurun_out/r2e_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         e=d.get("e2e") or {}
@@ -18,7 +18,7 @@ for f in sorted(glob.glob("gpurun_out/r2d_*.json")):
     except Exception as ex:
         print(f, "ERR", ex, open(f.replace(".json",".err")).read()[-400:])
 try:
-    rows=[r for r in csv.reader(open("gpurun_out/r2d_launches_c4s.csv")) if len(r)>5]
+    rows=[r for r in csv.reader(open("gpurun_out/r2e_launches_c4s.csv")) if len(r)>5]
     hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value"); ui=hdr.index("Metric Unit")
     agg=collections.OrderedDict()
     for r in rows[1:]:
