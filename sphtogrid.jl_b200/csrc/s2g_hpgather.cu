@@ -48,9 +48,7 @@ struct __align__(16) HRecS {
     double php;          // proj_h / ang_pix
     double an, anq;      // area_norm / (ang_pix Dx)^2  and the same times the quantity
     int rmin, rmax;      // disc rings
-    int big, nt;         // big: proj_h + 2 ang_pix >= 0.2 rad -> asin itself, not its series; nt: series coefficients
-    double c2in;         // squared chord below which A' = 1 (dx <= proj_h - ang_pix/2): no rim factor to evaluate
-    double pad2;
+    int big, pad1;       // big: proj_h + 2 ang_pix >= 0.2 rad -> asin itself, not its series
 };
 
 // asin(x)/x = 1 + x^2/6 + 3x^4/40 + ... written in c2 = (2x)^2 (the squared chord): G(c2) = sum kG[i] c2^i
@@ -402,13 +400,7 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                 s.php = r.ph * inv_ang;
                 s.an = r.an; s.anq = r.anq;
                 s.rmin = r.rmin; s.rmax = r.rmax;
-                const double pm = r.ph + 2.0 * g.ang_pix;
-                s.big = (pm < 0.2) ? 0 : 1;
-                // coefficients of G(c2) = asin(x)/x needed for a truncation error below 1e-16 (kG[n] c2max^n)
-                s.nt = pm < 0.031 ? 4 : (pm < 0.073 ? 5 : (pm < 0.13 ? 6 : 8));
-                const double si = sin(0.5 * fmax(r.ph - 0.5 * g.ang_pix, 0.0));
-                s.c2in = 4.0 * si * si * (1.0 - 1e-9);
-                s.pad2 = 0.0;
+                s.big = (r.ph + 2.0 * g.ang_pix < 0.2) ? 0 : 1; s.pad1 = 0;
                 s_rec[t] = s;
                 if (PASSA) s_part[t] = 0.0;
             }
@@ -429,8 +421,7 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                     c2[m] = fma(ex, ex, fma(ey, ey, ez2));
                     in[m] = c2[m] < c2max;
                 }
-                const double hinv = r.hinv, php = r.php, an = r.an, anq = r.anq, c2in = r.c2in;
-                const int nt = r.nt;
+                const double hinv = r.hinv, php = r.php, an = r.an, anq = r.anq;
                 double part = 0.0;
 #pragma unroll
                 for (int m = 0; m < HPG_PPT; ++m) {
@@ -441,37 +432,20 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                         const double hc = 0.5 * (c2[m] * y);
                         t = fma(-2.0 * asin(hc < 1.0 ? hc : 1.0), hinv, 1.0);
                     } else {
-                    const double sqh = (c2[m] * y) * hinv;        // chord / proj_h
-                        // G(c2) = asin(x)/x, x = chord/2, truncated per record (warp-uniform): small discs need 4 terms
-                        double G;
-                        if (nt == 4)
-                            G = fma(kG[3], c2[m], kG[2]);
-                        else {
-                            if (nt == 5)
-                                G = fma(kG[4], c2[m], kG[3]);
-                            else {
-                                if (nt == 6)
-                                    G = fma(kG[5], c2[m], kG[4]);
-                                else {
-                                    G = fma(kG[7], c2[m], kG[6]);
-                                    G = fma(G, c2[m], kG[5]);
-                                    G = fma(G, c2[m], kG[4]);
-                                }
-                                G = fma(G, c2[m], kG[3]);
-                            }
-                            G = fma(G, c2[m], kG[2]);
-                        }
+                        const double sqh = (c2[m] * y) * hinv;        // chord / proj_h
+                        double G = fma(kG[7], c2[m], kG[6]);
+                        G = fma(G, c2[m], kG[5]);
+                        G = fma(G, c2[m], kG[4]);
+                        G = fma(G, c2[m], kG[3]);
+                        G = fma(G, c2[m], kG[2]);
                         G = fma(G, c2[m], kG[1]);
                         G = fma(G, c2[m], kG[0]);
                         t = fma(-sqh, G, 1.0);
                     }
-                    double wk = hp_shape_t<KID>(t);
-                    // contributing_area (pixel_weights.jl:6-8): min(ang, |proj_h - (dx - ang/2)|)/ang = min(1, t php + 1/2);
-                    // it is 1 for every pixel of the group unless the group reaches the last half pixel before the rim
-                    if (__any_sync(0xffffffffu, in[m] && c2[m] > c2in)) {
-                        const double ap = fma(t, php, 0.5);
-                        wk *= ap < 1.0 ? ap : 1.0;
-                    }
+                    // contributing_area (pixel_weights.jl:6-8): min(ang, |proj_h - (dx - ang/2)|)/ang = min(1, t php + 1/2)
+                    const double ap = fma(t, php, 0.5);
+                    const double a1 = ap < 1.0 ? ap : 1.0;
+                    const double wk = hp_shape_t<KID>(t) * a1;
                     const double wka = in[m] ? wk : 0.0;
                     if (PASSA)
                         part += wka;
