@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Run under torchrun (one rank per GPU): sphMapping(parallel=True) — particles sharded by domain_decomposition, NCCL
-all-reduce of the partial flat images before reduce_image — must equal the single-GPU map and the CPU oracle."""
+"""Run under torchrun (one rank per GPU): sphMapping(parallel=True) — particles sharded into slices of equal summed
+footprint, partial flat images reduce-scattered over NCCL, reduce_image division on every rank's pixel slice, gather,
+transposition — must equal the single-GPU map and the CPU oracle.  Also: Float32 positions with Float64 fields,
+several quantities at once, `return_both_maps`."""
 import os
 import sys
 
@@ -41,5 +43,20 @@ for dims, kern in ((2, s2g.WendlandC6(2)), (3, s2g.Cubic(3))):
                               dimensions=dims)
         e2 = assert_parity(a, ref, what="parallel vs oracle")
         print(f"world={world} dims={dims}: parallel==serial (max rel {e:.1e}), vs oracle {e2:.1e}  OK", flush=True)
+# Float32 positions + Float64 fields, two quantities, both reduce_image settings, return_both_maps
+par = s2g.mappingParameters(**kw)
+pos32 = pos.astype(np.float32)
+Q = np.stack([q, np.sqrt(q + 1.0)], axis=1)
+for kwargs in (dict(reduce_image=True), dict(reduce_image=False), dict(return_both_maps=True)):
+    p1, p2 = pos32.copy(), pos32.copy()
+    a = s2g.sphMapping(p1, hsml, m, rho, Q, w, param=par, kernel=s2g.WendlandC4(2), calc_mean=True, parallel=True,
+                       show_progress=False, ctx=ctx, **kwargs)
+    b = s2g.sphMapping(p2, hsml, m, rho, Q, w, param=par, kernel=s2g.WendlandC4(2), calc_mean=True, parallel=False,
+                       show_progress=False, ctx=ctx, **kwargs)
+    assert np.array_equal(p1, p2) and p1.dtype == np.float32 and a.shape == b.shape
+    e = assert_parity(a, b, rtol=1e-12, what=f"mixed dtype, {kwargs}")
+    if rank == 0:
+        print(f"world={world} Float32 Pos + Float64 fields, 2 quantities, {kwargs}: parallel==serial (max rel {e:.1e})  OK",
+              flush=True)
 dist.barrier()
 dist.destroy_process_group()
