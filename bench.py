@@ -437,7 +437,7 @@ def run_workload(e, name, steps, warmup, main):
     fmax = torch.tensor([float(st["footprint_pixels"])], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
-    imb = float(fmax[0]) / max(fpx_all / world, 1.0) - 1.0
+    imb = (float(fmax[0]) / (fpx_all / world) - 1.0) if fpx_all > 0 else 0.0
     if stencil:
         n_mapped = n_total
     fpx, touched = int(st["footprint_pixels"]), int(st["touched_pixels"])
@@ -531,7 +531,10 @@ def run_workload(e, name, steps, warmup, main):
         fp64["frac"] = fp64["achieved"] / fp64["peak"]
         if stencil:
             n_red = planes * n_loc * stencil ** 3
-            red_peak, red_kind = lp["red_random_g"], "live random-address red.f64 microbenchmark over 1 GiB"
+            red_peak, red_kind = lp["red_rows_g"], ("live red.f64 microbenchmark, 32 consecutive doubles per warp (a "
+                                                    "stencil's reds fall on 2-3 consecutive cells of %d rows: the "
+                                                    "random-address rate, %.1f Gred/s over 1 GiB, is the other bracket)"
+                                                    % (stencil ** 2, lp["red_random_g"]))
         else:
             n_red = planes * touched
             red_peak, red_kind = lp["red_rows_g"], "live red.f64 microbenchmark, 32 consecutive doubles per warp"

@@ -554,6 +554,11 @@ __global__ void __launch_bounds__(256) k_hp_order_keys(s2g_particles P, HpGeom g
     idx[p] = (unsigned)p;
 }
 
+struct HpIsVal {
+    unsigned char v;
+    __host__ __device__ unsigned char operator()(unsigned char x) const { return x == v ? 1 : 0; }
+};
+
 template <int KID>
 int set_smem_attr(s2g_ctx* ctx, size_t smem)
 {
@@ -654,12 +659,26 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
         if (gather_on) {
             // the two gather lists reuse the list buffer (everything is stream-ordered): first the heavy discs
             // (pass A by a whole CTA each), then the ordinary ones (pass A by a warp each)
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < 3; ++pass) {
+                // 0: heavy discs, 1: ordinary discs from 0.073 rad (gath == 2), 2: small-angle discs (gath == 1, the
+                // bulk: short series instantiation of the gather kernels)
                 const bool heavy_pass = pass == 0;
                 if (heavy_pass && !coop_on) continue;
                 const int phl = s2g_phase_begin(ctx, PH_PREP);
-                S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)(heavy_pass ? d_gh : d_g),
-                                                    (unsigned*)d_list, (unsigned*)d_nh + 1, (int)P.n, ctx->stream));
+                if (heavy_pass) {
+                    S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)d_gh, (unsigned*)d_list,
+                                                        (unsigned*)d_nh + 1, (int)P.n, ctx->stream));
+                } else {
+                    cub::TransformInputIterator<unsigned char, HpIsVal, const unsigned char*> flags(
+                        (const unsigned char*)d_g, HpIsVal{(unsigned char)(pass == 1 ? 2 : 1)});
+                    size_t tb2 = 0;
+                    cub::DeviceSelect::Flagged(nullptr, tb2, ids, flags, (unsigned*)d_list, (unsigned*)d_nh + 1, (int)P.n,
+                                               ctx->stream);
+                    void* d_tmp2;
+                    S2G_TRY(s2g_scratch(ctx, "hp_heavy_tmp2", tb2 + 16, &d_tmp2));
+                    S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp2, tb2, ids, flags, (unsigned*)d_list, (unsigned*)d_nh + 1,
+                                                        (int)P.n, ctx->stream));
+                }
                 unsigned h_ng = 0;
                 S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_nh + 1, sizeof(unsigned), cudaMemcpyDeviceToHost,
                                          ctx->stream));
@@ -668,9 +687,9 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
                 ctx->launches += 1;
                 // discs above 0.2 rad need asin itself instead of its series: every heavy disc may, an ordinary one
                 // only when the heavy threshold lies above that (coarse maps)
-                const int big = heavy_pass || !coop_on || heavy_radius + 2.0 * g.ang_pix >= 0.2;
+                const int big = heavy_pass || (pass == 1 && (!coop_on || heavy_radius + 2.0 * g.ang_pix >= 0.2));
                 S2G_TRY(s2g_hp_gather_pipeline(ctx, P, nside, KID, calc_mean, (const unsigned*)d_list, (long long)h_ng,
-                                               (unsigned char*)d_s, amap, wmap, heavy_pass ? 1 : 0, big));
+                                               (unsigned char*)d_s, amap, wmap, heavy_pass ? 1 : 0, big, pass == 2 ? 5 : 8));
             }
         }
         d_skip = (const unsigned char*)d_s;

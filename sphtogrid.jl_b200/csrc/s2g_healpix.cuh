@@ -290,4 +290,4 @@ int s2g_hp_launch_records(s2g_ctx* ctx, const s2g_particles& P, long long nside,
                           const unsigned* list, long long n_list, HRec* recs, unsigned char* skip, int coop);
 int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
                            const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap,
-                           int coop_records, int big);
+                           int coop_records, int big, int nt);

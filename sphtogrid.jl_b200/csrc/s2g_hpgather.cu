@@ -63,7 +63,7 @@ __constant__ double kG[8] = {1.0,
 
 // ---- classification: which path deposits particle p
 //   heavy[p]      very large disc the gather cannot take (over a pole, ...) -> cooperative scatter launch
-//   gath[p]       ordinary disc for the tile-gather (pass A by a warp)
+//   gath[p]       ordinary disc for the tile-gather: 1 = below 0.073 rad (short series), 2 = up to the heavy threshold
 //   gath_heavy[p] very large disc for the tile-gather (pass A by a whole CTA)
 //   skip[p] = 1   the ordinary scatter launch must NOT take it (any of the three above)
 __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, int calc_mean,
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, 
             const bool ok = ph >= gather_radius && ph < 1.5 && theta - ph > m && theta + ph < kPi - m && isfinite(q) &&
                             isfinite(an_probe) && an_probe != 0.0;
             if (ok) {
-                if (h) { gh = 1; h = 0; } else ga = 1;
+                // ga = 1: small-angle disc (5 series coefficients are exact to 1e-16 below 0.073 rad), 2: the others
+                if (h) { gh = 1; h = 0; } else ga = (ph + m < 0.073) ? 1 : 2;
             }
         }
     }
@@ -314,7 +315,9 @@ __global__ void __launch_bounds__(256) k_hpg_tile_chunks(const unsigned* __restr
 // PASSA = true: calculate_weights (pixel_weights.jl:87-140) in the same tile form — per (tile, record) pair the CTA
 // sums wk·A' over the tile's pixels (warp shuffle, then shared-memory atomics across the 8 warps) and adds the pair's
 // partial sum to Ssum[record].  No pixel-centre trig per (pixel, particle), perfect load balance for huge discs.
-template <int KID, bool BIG, bool PASSA>
+// NT: coefficients of G(c2) = asin(x)/x kept (8: exact to 1e-16 up to 0.2 rad; 5: up to 0.073 rad, the bulk of a survey
+// volume — a compile-time constant: choosing it per record inside the loop cost more than it saved).
+template <int KID, bool BIG, bool PASSA, int NT>
 __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
                                                                      const unsigned* __restrict__ vals,
                                                                      const unsigned* __restrict__ tile_beg,
@@ -426,16 +429,27 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
 #pragma unroll
                 for (int m = 0; m < HPG_PPT; ++m) {
                     if (!__any_sync(0xffffffffu, in[m])) continue;   // this 16-pixel group of both rings is outside
-                    const double y = hp_rsqrt(c2[m]);
                     double t;                                         // 1 - u,  u = dx / proj_h
                     if (BIG && r.big) {                               // (warp-uniform) dx = 2 asin(chord / 2)
-                        const double hc = 0.5 * (c2[m] * y);
+                        const double hc = 0.5 * (c2[m] * hp_rsqrt(c2[m]));
                         t = fma(-2.0 * asin(hc < 1.0 ? hc : 1.0), hinv, 1.0);
                     } else {
-                        const double sqh = (c2[m] * y) * hinv;        // chord / proj_h
-                        double G = fma(kG[7], c2[m], kG[6]);
-                        G = fma(G, c2[m], kG[5]);
-                        G = fma(G, c2[m], kG[4]);
+                        // chord / proj_h = sqrt(c2)/h: MUFU seed y0, then the third-order correction applied to the
+                        // PRODUCT c2*y0/h (one instruction fewer than refining y0 first)
+                        double y0;
+                        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(c2[m]));
+                        const double sq0 = c2[m] * y0;
+                        const double e = fma(-sq0, y0, 1.0);
+                        const double ce = fma(e, kRsq[0], kRsq[1]) * e;
+                        const double sqh0 = sq0 * hinv;
+                        const double sqh = fma(ce, sqh0, sqh0);
+                        double G;
+                        if (NT >= 8) {
+                            G = fma(kG[7], c2[m], kG[6]);
+                            G = fma(G, c2[m], kG[5]);
+                            G = fma(G, c2[m], kG[4]);
+                        } else
+                            G = kG[4];
                         G = fma(G, c2[m], kG[3]);
                         G = fma(G, c2[m], kG[2]);
                         G = fma(G, c2[m], kG[1]);
@@ -490,14 +504,14 @@ long long env_ll(const char* name, long long dflt)
 template <int KID>
 int launch_gather_k(s2g_ctx* ctx, const HRec* recs, const unsigned* vals, const unsigned* tbeg, const unsigned* tend,
                     const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks, double* amap, double* wmap,
-                    int big, double* Ssum)
+                    int big, double* Ssum, int nt)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const int blocks = std::max((int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * (big ? 2 : HPG_CTAS)), 1);
-#define HPG_LAUNCH(B, A) k_hp_gather<KID, B, A><<<blocks, HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T, \
-                                                                                         chunks, amap, wmap, ctx->d_counters, Ssum)
-    if (Ssum) { if (big) HPG_LAUNCH(true, true); else HPG_LAUNCH(false, true); }
-    else      { if (big) HPG_LAUNCH(true, false); else HPG_LAUNCH(false, false); }
+#define HPG_LAUNCH(B, A, N) k_hp_gather<KID, B, A, N><<<blocks, HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T, \
+                                                                                               chunks, amap, wmap, ctx->d_counters, Ssum)
+    if (Ssum) { if (big) HPG_LAUNCH(true, true, 8); else if (nt >= 8) HPG_LAUNCH(false, true, 8); else HPG_LAUNCH(false, true, 5); }
+    else      { if (big) HPG_LAUNCH(true, false, 8); else if (nt >= 8) HPG_LAUNCH(false, false, 8); else HPG_LAUNCH(false, false, 5); }
 #undef HPG_LAUNCH
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
@@ -505,10 +519,10 @@ int launch_gather_k(s2g_ctx* ctx, const HRec* recs, const unsigned* vals, const 
 
 int launch_gather(s2g_ctx* ctx, int kernel, const HRec* recs, const unsigned* vals, const unsigned* tbeg,
                   const unsigned* tend, const unsigned* cbeg, const HpGeom& g, const HpTiles& T, unsigned chunks,
-                  double* amap, double* wmap, int big, double* Ssum)
+                  double* amap, double* wmap, int big, double* Ssum, int nt)
 {
     switch (kernel) {
-#define HPG_CASE(K) case K: return launch_gather_k<K>(ctx, recs, vals, tbeg, tend, cbeg, g, T, chunks, amap, wmap, big, Ssum);
+#define HPG_CASE(K) case K: return launch_gather_k<K>(ctx, recs, vals, tbeg, tend, cbeg, g, T, chunks, amap, wmap, big, Ssum, nt);
         HPG_CASE(S2G_KERNEL_CUBIC)
         HPG_CASE(S2G_KERNEL_QUINTIC)
         HPG_CASE(S2G_KERNEL_WENDLAND_C2)
@@ -569,7 +583,7 @@ int s2g_hp_classify(s2g_ctx* ctx, const s2g_particles& P, long long nside, int c
 // normalisation) get skip[p] = 0 there and are deposited by the scatter launch that FOLLOWS this call.
 int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
                            const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap,
-                           int coop_records, int big)
+                           int coop_records, int big, int nt)
 {
     if (n_list <= 0) return S2G_OK;
     const HpGeom g = make_hp(nside);
@@ -672,7 +686,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
                 const int pha = s2g_phase_begin(ctx, PH_NORM);
                 int rca = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
                                         (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
-                                        (double*)d_S);
+                                        (double*)d_S, nt);
                 if (rca == S2G_OK) {
                     k_hp_normalise<<<(int)((nb + 255) / 256), 256, 0, st>>>((HRec*)d_recs, (const double*)d_S, nb, skip);
                     k_hpg_count<<<(int)((nb + 255) / 256), 256, 0, st>>>((const HRec*)d_recs, nb, ctx->d_counters);
@@ -685,7 +699,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
             const int rc = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
                                          (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
-                                         nullptr);
+                                         nullptr, nt);
             s2g_phase_end(ctx, phg);
             S2G_TRY(rc);
             ctx->launches += 1;
