@@ -583,7 +583,7 @@ int s2g_hp_classify(s2g_ctx* ctx, const s2g_particles& P, long long nside, int c
 // normalisation) get skip[p] = 0 there and are deposited by the scatter launch that FOLLOWS this call.
 int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside, int kernel, int calc_mean,
                            const unsigned* list, long long n_list, unsigned char* skip, double* amap, double* wmap,
-                           int coop_records, int big, int nt)
+                           int coop_records, int big, int series_nt)
 {
     if (n_list <= 0) return S2G_OK;
     const HpGeom g = make_hp(nside);
@@ -686,7 +686,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
                 const int pha = s2g_phase_begin(ctx, PH_NORM);
                 int rca = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
                                         (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
-                                        (double*)d_S, nt);
+                                        (double*)d_S, series_nt);
                 if (rca == S2G_OK) {
                     k_hp_normalise<<<(int)((nb + 255) / 256), 256, 0, st>>>((HRec*)d_recs, (const double*)d_S, nb, skip);
                     k_hpg_count<<<(int)((nb + 255) / 256), 256, 0, st>>>((const HRec*)d_recs, nb, ctx->d_counters);
@@ -699,7 +699,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
             const int rc = launch_gather(ctx, kernel, (const HRec*)d_recs, (const unsigned*)d_vals2, (const unsigned*)d_tbeg,
                                          (const unsigned*)d_tend, (const unsigned*)d_cbeg, g, T, h_chunks, amap, wmap, big,
-                                         nullptr, nt);
+                                         nullptr, series_nt);
             s2g_phase_end(ctx, phg);
             S2G_TRY(rc);
             ctx->launches += 1;
