@@ -33,7 +33,6 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     const double dz_lo = overlap_1d(r.z, r.h, r.lo[2]), dz_hi = overlap_1d(r.z, r.h, r.hi[2]);
     const double hinv = r.hinv;
     const double xb = center_dist(r.x, (double)r.lo[0]) * hinv;  // a of the first i-plane
-    const double aq[4] = {0.0, -hinv, -2.0 * hinv, -3.0 * hinv};
 
     // ---- pass A (calculate_weights, cic_3D.jl:13-78); loops are warp-uniform (lanes without a column idle) so that
     // the list compaction can ballot
@@ -60,22 +59,19 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
             for (int ii = 0; ii < ni; ii += 4) {
                 double wk[4];
                 bool in[4];
-                // one int->double conversion per group of four cells (the XU pipe that converts is also the MUFU pipe)
-                const double ab = fma(-(double)ii, hinv, xb);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double a = ab + aq[q];
+                    const double a = fma(-(double)(ii + q), hinv, xb);
                     const double s = fma(a, a, bc2);
                     in[q] = colv && below_one(s) && (ii + q < ni);
                     wk[q] = shape_s<KID>(s);
                 }
-                const bool edge = (ii == 0) || (ii + 3 >= ni - 1);   // uniform: the group holds the first / last i-plane
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = r.lo[0] + ii + q;
-                    const double dx = !edge ? 1.0 : ((i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0));
+                    const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
                     const double wq = select_or_zero(in[q], wk[q]);
-                    col = edge ? fma(wq, dx, col) : col + wq;
+                    col = fma(wq, dx, col);
                     cnt += in[q] ? 1 : 0;
                     if (cache) {
                         const double gq = wq * (dx * dydz);     // the cell's wk·dV of pass B
@@ -189,10 +185,9 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
             for (int ii = 0; ii < ni; ii += 4) {
                 double wk[4];
                 bool in[4];
-                const double ab = fma(-(double)ii, hinv, xb);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double a = ab + aq[q];
+                    const double a = fma(-(double)(ii + q), hinv, xb);
                     const double s = fma(a, a, bc2);
                     in[q] = below_one(s) && (ii + q < ni);
                     wk[q] = shape_s<KID>(s);
