@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
 {
     __shared__ HRecS s_rec[HPG_BATCH];
     __shared__ double s_part[PASSA ? HPG_BATCH : 1];
+    // pass A: the lanes' partial sums of 8 records are parked here and reduced together (8 loads + 7 adds + 2 shuffle
+    // steps per lane for 8 records, instead of 5 shuffle steps per record); 33-double rows: at most 2-way bank conflicts
+    __shared__ double s_red[PASSA ? 8 : 1][PASSA ? 8 : 1][PASSA ? 33 : 1];
     __shared__ unsigned s_work[4];
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const int rt = tid >> 4, l16 = tid & 15;   // ring of the tile, lane within the ring
@@ -408,6 +411,19 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                 if (PASSA) s_part[t] = 0.0;
             }
             __syncthreads();
+            int kslot = 0, my_e = 0;   // pass A: records parked in s_red[wq]; lane k remembers the record of slot k
+            auto flush_slots = [&]() {
+                __syncwarp();
+                const int k = lane & 7, c0 = (lane >> 3) * 8;
+                double sum = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum += s_red[PASSA ? wq : 0][PASSA ? k : 0][PASSA ? c0 + j : 0];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                if (lane < kslot && sum != 0.0) atomicAdd(&s_part[PASSA ? my_e : 0], sum);
+                kslot = 0;
+                __syncwarp();
+            };
             for (int e = 0; e < nb; ++e) {
                 const HRecS& r = s_rec[e];
                 if (wr_hi < r.rmin || wr_lo > r.rmax) continue;   // warp-uniform: none of this warp's rings in the disc
@@ -469,9 +485,14 @@ __global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(c
                     }
                 }
                 if (PASSA) {
-                    part = warp_sum(part);
-                    if (lane == 0 && part != 0.0) atomicAdd(&s_part[e], part);
+                    s_red[PASSA ? wq : 0][PASSA ? kslot : 0][PASSA ? lane : 0] = part;
+                    if (lane == kslot) my_e = e;
+                    if (++kslot == 8) flush_slots();
                 }
+            }
+            if (PASSA && kslot > 0) {
+                // unused slots hold stale numbers: only lanes < kslot add their sum
+                flush_slots();
             }
             if (PASSA) {
                 __syncthreads();
