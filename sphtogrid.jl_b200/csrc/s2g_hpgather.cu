@@ -176,10 +176,16 @@ __global__ void __launch_bounds__(256) k_hp_normalise(HRec* __restrict__ recs, c
 // The sector range of a ring is that of its query_disc pixel run (ring_run: the reference's own list), the band's
 // range the union over its rings, expressed relative to the sector holding the disc centre (the runs are intervals
 // around the particle's azimuth, possibly wrapping).
+// The count pass parks (first sector, sector count) of every band of a record in `bandinfo` (HPG_NBMAX slots per record),
+// so that the write pass of a record with at most HPG_NBMAX bands (every non-heavy disc) copies them out instead of
+// evaluating the ring runs (an atan2 per ring) a second time.
+constexpr int HPG_NBMAX = 40;
+
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k_hp_pairs(HRec* __restrict__ recs, long long n_rec, HpGeom g, HpTiles T,
                                                   const unsigned* __restrict__ off, unsigned* __restrict__ npairs,
-                                                  unsigned* __restrict__ keys, unsigned* __restrict__ vals, int fill_ntot)
+                                                  unsigned* __restrict__ keys, unsigned* __restrict__ vals, int fill_ntot,
+                                                  unsigned* __restrict__ bandinfo)
 {
     const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
     const long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -187,6 +193,23 @@ __global__ void __launch_bounds__(256) k_hp_pairs(HRec* __restrict__ recs, long 
     const HRec r = recs[t];
     if (r.rmin > r.rmax) {
         if (!WRITE && lane == 0) npairs[t] = 0;
+        return;
+    }
+    if (WRITE && bandinfo && (r.rmax - 1) / HPG_BR - (r.rmin - 1) / HPG_BR < HPG_NBMAX) {
+        // replay the parked band ranges: lanes over the sectors of a band
+        const int b0 = (r.rmin - 1) / HPG_BR, b1 = (r.rmax - 1) / HPG_BR;
+        unsigned o = off[t];
+        for (int band = b0; band <= b1; ++band) {
+            const unsigned bi = bandinfo[t * HPG_NBMAX + (band - b0)];
+            const int sec0 = (int)(bi >> 16), nsec = (int)(bi & 0xffffu), ns = T.band_ns[band], base = T.band_base[band];
+            for (int k = lane; k < nsec; k += 32) {
+                int sec = sec0 + k;
+                if (sec >= ns) sec -= ns;
+                keys[o + k] = (unsigned)(base + sec);
+                vals[o + k] = (unsigned)t;
+            }
+            o += (unsigned)nsec;
+        }
         return;
     }
     Disc d;
@@ -247,6 +270,11 @@ __global__ void __launch_bounds__(256) k_hp_pairs(HRec* __restrict__ recs, long 
             hi_rel = max(hi_rel, __shfl_xor_sync(0xffffffffu, hi_rel, s));
         }
         int nsec = (band_ok && hi_rel >= lo_rel) ? min(ns, hi_rel - lo_rel + 1) : 0;
+        if (!WRITE && bandinfo && band_ok && l16 == 0 && band - b0 < HPG_NBMAX) {
+            int sec0 = (kref + lo_rel) % ns;
+            if (sec0 < 0) sec0 += ns;
+            bandinfo[t * HPG_NBMAX + (band - b0)] = ((unsigned)sec0 << 16) | (unsigned)nsec;
+        }
         // the other half-warp's count, to keep the two bands' outputs in order
         const int n_other = __shfl_xor_sync(0xffffffffu, nsec, 16);
         const int base = T.band_base[band_ok ? band : 0];
@@ -638,8 +666,10 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
         ph = s2g_phase_begin(ctx, PH_SORT);
         S2G_CUDA(cudaMemsetAsync((unsigned*)d_np + nb, 0, sizeof(unsigned), st));
         const int wblocks = (int)((nb * 32 + 255) / 256);
+        void* d_bi = nullptr;
+        S2G_TRY(s2g_scratch(ctx, "hpg_bandinfo", sizeof(unsigned) * (size_t)nb * HPG_NBMAX, &d_bi));
         k_hp_pairs<false><<<wblocks, 256, 0, st>>>((HRec*)d_recs, nb, g, T, nullptr, (unsigned*)d_np, nullptr, nullptr,
-                                                   passa_gather ? 1 : 0);
+                                                   passa_gather ? 1 : 0, (unsigned*)d_bi);
         S2G_CUDA(cudaGetLastError());
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, (const unsigned*)d_np, (unsigned*)d_off, (int)(nb + 1), st);
@@ -673,7 +703,7 @@ int s2g_hp_gather_pipeline(s2g_ctx* ctx, const s2g_particles& P, long long nside
             S2G_TRY(s2g_scratch(ctx, "hpg_nch", sizeof(unsigned) * (nt + 1), &d_nch));
             S2G_TRY(s2g_scratch(ctx, "hpg_cbeg", sizeof(unsigned) * (nt + 1), &d_cbeg));
             k_hp_pairs<true><<<wblocks, 256, 0, st>>>((HRec*)d_recs, nb, g, T, (const unsigned*)d_off, nullptr,
-                                                      (unsigned*)d_keys, (unsigned*)d_vals, 0);
+                                                      (unsigned*)d_keys, (unsigned*)d_vals, 0, (unsigned*)d_bi);
             S2G_CUDA(cudaGetLastError());
             int bits = 1;
             while ((1 << bits) < nt) ++bits;
