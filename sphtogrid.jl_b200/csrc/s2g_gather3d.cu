@@ -374,6 +374,7 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
               ntk = (int)((G.npix + T_K - 1) / T_K);
     const long long ntiles_ll = (long long)nti * ntj * ntk;
     if (ctx->strategy == S2G_STRATEGY_SCATTER || ntiles_ll > (1LL << 30)) {
+        S2G_TRY(s2g_stage_wait(ctx, P.n));
         return s2g_launch_scatter_3d(ctx, P, G, kernel, nullptr, P.n, image);  // times itself (PH_DEPOSIT)
     }
     const int ntiles = (int)ntiles_ll;
@@ -381,7 +382,10 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
     long long p0 = 0;
     long long batch = std::min(batch_max, (long long)P.n);
     while (p0 < P.n) {
-        const long long nb = std::min(batch, (long long)P.n - p0);
+        long long nb = std::min(batch, (long long)P.n - p0);
+        // overlapped staging (s2g_api.cu): small first slice, every slice waits for exactly the particles it reads
+        if (p0 == 0 && s2g_stage_first_slice(ctx) > 0) nb = std::min(nb, s2g_stage_first_slice(ctx));
+        S2G_TRY(s2g_stage_wait(ctx, p0 + nb));
         void *d_cls, *d_np, *d_ps, *d_pg, *d_ls, *d_lg, *d_tmp, *d_sum;
         S2G_TRY(s2g_scratch(ctx, "g_cls", sizeof(int) * (nb + 1), &d_cls));
         S2G_TRY(s2g_scratch(ctx, "g_np", sizeof(unsigned) * (nb + 1), &d_np));
@@ -412,12 +416,13 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
         S2G_CUDA(cub::DeviceReduce::Sum(d_tmp, tb, it_np, (unsigned long long*)d_sum, (int)nb, st));
         unsigned h_ns = 0, h_ng = 0;
         unsigned long long h_ub = 0;
-        S2G_CUDA(cudaMemcpyAsync(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        S2G_CUDA(cudaMemcpyAsync(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        S2G_CUDA(cudaMemcpyAsync(&h_ub, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        s2g_readback rb(ctx);
+        S2G_CUDA(rb.add(&h_ns, (unsigned*)d_ps + nb, sizeof(unsigned)));
+        S2G_CUDA(rb.add(&h_ng, (unsigned*)d_pg + nb, sizeof(unsigned)));
+        S2G_CUDA(rb.add(&h_ub, d_sum, sizeof(unsigned long long)));
         s2g_phase_end(ctx, ph);
         ctx->launches += 4;
-        S2G_CUDA(cudaStreamSynchronize(st));
+        S2G_CUDA(rb.sync());
         if ((long long)h_ub > pair_cap && nb > 1024) {
             batch = std::max<long long>(1024, nb / 2);
             continue;
@@ -455,10 +460,9 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
             S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb4, (const unsigned*)d_npg, (unsigned*)d_off, (int)(n_g + 1), st));
             unsigned h_m = 0;
             unsigned long long h_rr = 0;
-            S2G_CUDA(cudaMemcpyAsync(&h_m, (unsigned*)d_off + n_g, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            S2G_CUDA(cudaMemcpyAsync(&h_rr, ctx->d_counters + CNT_PAIRS, sizeof(unsigned long long),
-                                     cudaMemcpyDeviceToHost, st));
-            S2G_CUDA(cudaStreamSynchronize(st));
+            S2G_CUDA(rb.add(&h_m, (unsigned*)d_off + n_g, sizeof(unsigned)));
+            S2G_CUDA(rb.add(&h_rr, ctx->d_counters + CNT_PAIRS, sizeof(unsigned long long)));
+            S2G_CUDA(rb.sync());
             const long long m = h_m;
             if (h_rr > 0) {
                 s2g_phase_end(ctx, ph);
@@ -501,11 +505,11 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
                 size_t tbb = tb3 + 16;
                 S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tbb, (const unsigned*)d_nch, (unsigned*)d_cbeg, ntiles + 1, st));
                 unsigned h_chunks = 0;
-                S2G_CUDA(cudaMemcpyAsync(&h_chunks, (unsigned*)d_cbeg + ntiles, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                S2G_CUDA(rb.add(&h_chunks, (unsigned*)d_cbeg + ntiles, sizeof(unsigned)));
                 s2g_phase_end(ctx, ph);
                 ph = -1;
                 ctx->launches += 8;
-                S2G_CUDA(cudaStreamSynchronize(st));
+                S2G_CUDA(rb.sync());
                 S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), st));
                 const int phg = s2g_phase_begin(ctx, PH_DEPOSIT);
                 const int gblocks = (int)std::min<long long>((long long)h_chunks, (long long)ctx->sm_count * 3);
@@ -530,7 +534,6 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
 int s2g_launch_deposit_3d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, int kernel, double* image)
 {
     if (P.n <= 0) return S2G_OK;
-    S2G_TRY(s2g_stage_wait(ctx, P.n));   // inputs may still be on their way (overlapped staging, s2g_api.cu)
     switch (kernel) {
     case S2G_KERNEL_CUBIC: return deposit3d_k<S2G_KERNEL_CUBIC>(ctx, P, G, image);
     case S2G_KERNEL_QUINTIC: return deposit3d_k<S2G_KERNEL_QUINTIC>(ctx, P, G, image);

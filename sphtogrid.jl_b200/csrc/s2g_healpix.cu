@@ -660,10 +660,9 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
             // the two gather lists reuse the list buffer (everything is stream-ordered): first the heavy discs
             // (pass A by a whole CTA each), then the ordinary ones (pass A by a warp each)
             for (int pass = 0; pass < 3; ++pass) {
-                // 0: heavy discs, 1: ordinary discs from 0.073 rad (gath == 2), 2: small-angle discs (gath == 1, the
-                // bulk: short series instantiation of the gather kernels)
+                // 0: discs above 0.2 rad (asin), 1: discs from 0.073 rad (gath == 2, 8 series coefficients), 2: small-angle
+                // discs (gath == 1, the bulk: 5 coefficients)
                 const bool heavy_pass = pass == 0;
-                if (heavy_pass && !coop_on) continue;
                 const int phl = s2g_phase_begin(ctx, PH_PREP);
                 if (heavy_pass) {
                     S2G_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, ids, (const unsigned char*)d_gh, (unsigned*)d_list,
@@ -685,9 +684,7 @@ int launch_healpix_k(s2g_ctx* ctx, const s2g_particles& P, long long nside, int 
                 s2g_phase_end(ctx, phl);
                 S2G_CUDA(cudaStreamSynchronize(ctx->stream));
                 ctx->launches += 1;
-                // discs above 0.2 rad need asin itself instead of its series: every heavy disc may, an ordinary one
-                // only when the heavy threshold lies above that (coarse maps)
-                const int big = heavy_pass || (pass == 1 && (!coop_on || heavy_radius + 2.0 * g.ang_pix >= 0.2));
+                const int big = heavy_pass ? 1 : 0;   // the classification sends every disc above 0.2 rad to pass 0
                 S2G_TRY(s2g_hp_gather_pipeline(ctx, P, nside, KID, calc_mean, (const unsigned*)d_list, (long long)h_ng,
                                                (unsigned char*)d_s, amap, wmap, heavy_pass ? 1 : 0, big, pass == 2 ? 5 : 8));
             }

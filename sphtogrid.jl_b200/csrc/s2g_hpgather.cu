@@ -63,8 +63,8 @@ __constant__ double kG[8] = {1.0,
 
 // ---- classification: which path deposits particle p
 //   heavy[p]      very large disc the gather cannot take (over a pole, ...) -> cooperative scatter launch
-//   gath[p]       ordinary disc for the tile-gather: 1 = below 0.073 rad (short series), 2 = up to the heavy threshold
-//   gath_heavy[p] very large disc for the tile-gather (pass A by a whole CTA)
+//   gath[p]       disc for the tile-gather: 1 = below 0.073 rad (short series), 2 = up to 0.2 rad
+//   gath_heavy[p] disc above 0.2 rad for the tile-gather (asin instead of its series)
 //   skip[p] = 1   the ordinary scatter launch must NOT take it (any of the three above)
 __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, int calc_mean,
                                                      const unsigned char* __restrict__ take, double heavy_radius,
@@ -92,8 +92,10 @@ __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, 
             const bool ok = ph >= gather_radius && ph < 1.5 && theta - ph > m && theta + ph < kPi - m && isfinite(q) &&
                             isfinite(an_probe) && an_probe != 0.0;
             if (ok) {
-                // ga = 1: small-angle disc (5 series coefficients are exact to 1e-16 below 0.073 rad), 2: the others
-                if (h) { gh = 1; h = 0; } else ga = (ph + m < 0.073) ? 1 : 2;
+                // ga = 1: small-angle disc (5 series coefficients are exact to 1e-16 below 0.073 rad), 2: up to 0.2 rad
+                // (8 coefficients); gh: above — asin itself (BIG instantiation, 2 CTAs/SM)
+                if (ph + m >= 0.2) gh = 1; else ga = (ph + m < 0.073) ? 1 : 2;
+                h = 0;
             }
         }
     }
