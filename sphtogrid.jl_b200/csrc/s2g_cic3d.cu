@@ -15,7 +15,13 @@
 // k-contiguous order), so that pass B neither re-evaluates the kernel (cic_3D.jl:172-188 recomputes nothing either:
 // the reference keeps wk[] and V[] from calculate_weights) nor walks the empty corners of the bounding box: all 32
 // lanes issue reds.  A particle with more non-zero cells than S3_CAP (h > ~6 cells) takes the two-pass path.
-constexpr int S3_CAP = 1024;
+#ifndef S2G_3D_CAP
+#define S2G_3D_CAP 1024
+#endif
+#ifndef S2G_3D_MINB
+#define S2G_3D_MINB 1     // min CTAs/SM of k_scatter3d (register cap): -DS2G_3D_MINB=3 -DS2G_3D_CAP=640 is the A/B variant
+#endif
+constexpr int S3_CAP = S2G_3D_CAP;
 
 template <int KID>
 __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G, int lane,
@@ -211,7 +217,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
 }
 
 template <int KID>
-__global__ void __launch_bounds__(256) k_scatter3d(s2g_particles P, s2g_geom G, const unsigned* __restrict__ order,
+__global__ void __launch_bounds__(256, S2G_3D_MINB) k_scatter3d(s2g_particles P, s2g_geom G, const unsigned* __restrict__ order,
                                                    long long n_list, double* __restrict__ image,
                                                    unsigned long long* __restrict__ counters, int use_cache)
 {
