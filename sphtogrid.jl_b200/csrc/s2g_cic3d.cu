@@ -23,11 +23,39 @@
 #endif
 constexpr int S3_CAP = S2G_3D_CAP;
 
-template <int KID>
+// Where pass B puts a cell's two contributions.  TILE: a CTA-owned shared-memory tile of T3^3 cells x 2 planes around
+// the 8^3 block the particle's centre lies in (k_scatter3d_tile): shared-memory atomics instead of L2 reds, one flush of
+// the tile per work item; cells of a large kernel that reach beyond the tile still go to the image directly.
+constexpr int T3 = 24;          // tile edge: an 8^3 block + a halo of 8 cells on every side
+constexpr int B3 = 8;           // block edge
+struct Sink3 {
+    double* tile;               // T3^3 x 2 doubles, (weight, quantity) interleaved
+    int oi, oj, ok;             // image cell of tile cell (0,0,0)
+};
+
+template <bool TILE>
+__device__ __forceinline__ void deposit_cell(const Sink3& sk, double* __restrict__ image, long long npl, long long n, int i,
+                                             int j, int k, double w, double q)
+{
+    if (TILE) {
+        const unsigned ti = (unsigned)(i - sk.oi), tj = (unsigned)(j - sk.oj), tk = (unsigned)(k - sk.ok);
+        if (ti < (unsigned)T3 && tj < (unsigned)T3 && tk < (unsigned)T3) {
+            double* c = sk.tile + 2 * ((ti * T3 + tj) * T3 + tk);
+            atomicAdd(c, w);
+            atomicAdd(c + 1, q);
+            return;
+        }
+    }
+    const long long idx = ((long long)i * n + j) * n + k;   // indices.jl:15-17
+    red_add(image + npl + idx, w);
+    red_add(image + idx, q);
+}
+
+template <int KID, bool TILE>
 __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G, int lane,
                                                 double* __restrict__ image, unsigned long long& touched,
                                                 unsigned long long& fallback, double* __restrict__ s_w,
-                                                unsigned* __restrict__ s_c)
+                                                unsigned* __restrict__ s_c, const Sink3& sk)
 {
     const int ni = r.hi[0] - r.lo[0] + 1, nj = r.hi[1] - r.lo[1] + 1, nk = r.hi[2] - r.lo[2] + 1;
     const int lw = nk >= 32 ? 5 : (nk <= 1 ? 0 : 32 - __clz(nk - 1));
@@ -149,9 +177,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                     const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
                     const double pw = wk * (dx * dy * dz) * volume_norm;
                     if (pw != 0.0) {
-                        const long long idx = (long long)i * n * n + (long long)j * n + k;
-                        red_add(image + npl + idx, pw);
-                        red_add(image + idx, r.q * pw);
+                        deposit_cell<false>(sk, image, npl, n, i, j, k, pw, r.q * pw);   // rare: straight to the image
                         ++touched;
                     }
                 }
@@ -168,9 +194,14 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
         for (int t = lane; t < n_list; t += 32) {
             const double g = s_w[t];
             const unsigned c = s_c[t];
-            const long long idx = o0 + (long long)(c >> 16) * n * n + (long long)((c >> 8) & 255u) * n + (c & 255u);
-            red_add(image + npl + idx, g * volume_norm);
-            red_add(image + idx, g * vq);
+            if (TILE)
+                deposit_cell<true>(sk, image, npl, n, r.lo[0] + (int)(c >> 16), r.lo[1] + (int)((c >> 8) & 255u),
+                                   r.lo[2] + (int)(c & 255u), g * volume_norm, g * vq);
+            else {
+                const long long idx = o0 + (long long)(c >> 16) * n * n + (long long)((c >> 8) & 255u) * n + (c & 255u);
+                red_add(image + npl + idx, g * volume_norm);
+                red_add(image + idx, g * vq);
+            }
         }
         if (lane == 0) touched += (unsigned long long)n_list;
         __syncwarp();   // the list is reused by the next particle
@@ -205,9 +236,13 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                     const double dx = (i == r.lo[0]) ? dx_lo : ((i == r.hi[0]) ? dx_hi : 1.0);
                     const double g = wk[q] * (dx * dydz);
                     if (nonzero_bits(g)) {
-                        const long long idx = (long long)i * n * n;  // indices.jl:15-17
-                        red_add(base + npl + idx, g * volume_norm);
-                        red_add(base + idx, g * vq);
+                        if (TILE)
+                            deposit_cell<true>(sk, image, npl, n, i, j, k, g * volume_norm, g * vq);
+                        else {
+                            const long long idx = (long long)i * n * n;  // indices.jl:15-17
+                            red_add(base + npl + idx, g * volume_norm);
+                            red_add(base + idx, g * vq);
+                        }
                         ++touched;
                     }
                 }
@@ -246,7 +281,7 @@ __global__ void __launch_bounds__(256, S2G_3D_MINB) k_scatter3d(s2g_particles P,
                 fpx += (unsigned long long)(r.hi[0] - r.lo[0] + 1) * (unsigned long long)(r.hi[1] - r.lo[1] + 1) *
                        (unsigned long long)(r.hi[2] - r.lo[2] + 1);
             }
-            warp_deposit_3d<KID>(r, G, lane, image, touched, fallback, s_w, s_c);
+            warp_deposit_3d<KID, false>(r, G, lane, image, touched, fallback, s_w, s_c, Sink3{nullptr, 0, 0, 0});
         }
     }
     touched = (unsigned long long)warp_sum_ll((long long)touched);
@@ -257,6 +292,197 @@ __global__ void __launch_bounds__(256, S2G_3D_MINB) k_scatter3d(s2g_particles P,
         if (mapped) atomicAdd(&counters[CNT_SCATTER], mapped);
         if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
     }
+}
+
+// ---- block-per-block scatter with a shared-memory image tile (north_star (3): "block-per-particle with shared-memory
+// image tiles for large footprints, flushed with red adds").  Particles are sorted by the 8^3-cell block of their centre;
+// a CTA takes a block (a chunk of <= TILE_CH of its particles), zeroes a 24^3 x 2 tile in shared memory (216 KB, one
+// CTA per SM), lets its 16 warps deposit one particle each — pass A as before, pass B with shared-memory atomics — and
+// flushes the tile once.  C3: ~250 particles x ~1200 cells x 2 planes per block become 27 648 reds instead of 600 000.
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_CH = 2048;
+
+__global__ void __launch_bounds__(256) k_tile3_keys(s2g_particles P, s2g_geom G, const unsigned* __restrict__ list,
+                                                    long long n_list, int nb8, unsigned* __restrict__ keys,
+                                                    unsigned* __restrict__ idx)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_list) return;
+    const long long p = list ? (long long)list[t] : t;
+    unsigned key = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double x = fma(ld_pos(P, p, d), G.len2pix, G.half_n);
+        int b = (int)floor(x * (1.0 / B3));
+        b = min(max(b, 0), nb8 - 1);
+        key = key * (unsigned)nb8 + (unsigned)b;
+    }
+    keys[t] = key;
+    idx[t] = (unsigned)p;
+}
+
+__global__ void __launch_bounds__(256) k_tile3_bounds(const unsigned* __restrict__ keys, long long m,
+                                                      unsigned* __restrict__ beg, unsigned* __restrict__ end)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const unsigned k = keys[t];
+    if (t == 0 || keys[t - 1] != k) beg[k] = (unsigned)t;
+    if (t == m - 1 || keys[t + 1] != k) end[k] = (unsigned)(t + 1);
+}
+
+__global__ void __launch_bounds__(256) k_tile3_chunks(const unsigned* __restrict__ beg, const unsigned* __restrict__ end,
+                                                      int nkeys, unsigned* __restrict__ nch)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeys) return;
+    nch[t] = (end[t] - beg[t] + TILE_CH - 1) / TILE_CH;
+}
+
+template <int KID>
+__global__ void __launch_bounds__(TILE_THREADS, 1) k_scatter3d_tile(s2g_particles P, s2g_geom G,
+                                                                    const unsigned* __restrict__ sorted_idx,
+                                                                    const unsigned* __restrict__ beg,
+                                                                    const unsigned* __restrict__ end,
+                                                                    const unsigned* __restrict__ chunk_begin, int nkeys,
+                                                                    int nb8, unsigned total_chunks,
+                                                                    double* __restrict__ image,
+                                                                    unsigned long long* __restrict__ counters)
+{
+    extern __shared__ __align__(16) double s_tile[];   // T3^3 x 2
+    __shared__ unsigned s_work[3];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    constexpr int NW = TILE_THREADS / 32;
+    constexpr int NCELL = T3 * T3 * T3;
+    unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
+    const long long n = G.npix, npl = n * n * n;
+    for (;;) {
+        if (tid == 0) {
+            const unsigned w = (unsigned)atomicAdd(&counters[CNT_WORK], 1ull);
+            unsigned key = 0xffffffffu, b = 0, e = 0;
+            if (w < total_chunks) {
+                int lo = 0, hi = nkeys;  // last key with chunk_begin[key] <= w
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (chunk_begin[mid] <= w) lo = mid; else hi = mid;
+                }
+                key = (unsigned)lo;
+                b = beg[lo] + (w - chunk_begin[lo]) * TILE_CH;
+                e = min(b + TILE_CH, end[lo]);
+            }
+            s_work[0] = key; s_work[1] = b; s_work[2] = e;
+        }
+        for (int c = tid; c < 2 * NCELL; c += TILE_THREADS) s_tile[c] = 0.0;
+        __syncthreads();
+        const unsigned key = s_work[0], wb = s_work[1], we = s_work[2];
+        if (key == 0xffffffffu) break;
+        Sink3 sk;
+        sk.tile = s_tile;
+        sk.ok = (int)(key % (unsigned)nb8) * B3 - (T3 - B3) / 2;
+        sk.oj = (int)((key / (unsigned)nb8) % (unsigned)nb8) * B3 - (T3 - B3) / 2;
+        sk.oi = (int)(key / ((unsigned)nb8 * (unsigned)nb8)) * B3 - (T3 - B3) / 2;
+        for (unsigned t = wb + wq; t < we; t += NW) {
+            const long long p = sorted_idx[t];
+            Rec3 r;
+            if (!make_rec3(P, G, p, r)) continue;
+            if (lane == 0) {
+                ++mapped;
+                fpx += (unsigned long long)(r.hi[0] - r.lo[0] + 1) * (unsigned long long)(r.hi[1] - r.lo[1] + 1) *
+                       (unsigned long long)(r.hi[2] - r.lo[2] + 1);
+            }
+            warp_deposit_3d<KID, true>(r, G, lane, image, touched, fallback, nullptr, nullptr, sk);
+        }
+        __syncthreads();
+        // flush: tile cell (ti, tj, tk) -> image cell (oi+ti, oj+tj, ok+tk); tk is the contiguous axis
+        for (int c = tid; c < NCELL; c += TILE_THREADS) {
+            const double w = s_tile[2 * c], q = s_tile[2 * c + 1];
+            if (w != 0.0 || q != 0.0) {
+                const int tk = c % T3, tj = (c / T3) % T3, ti = c / (T3 * T3);
+                const long long gi = sk.oi + ti, gj = sk.oj + tj, gk = sk.ok + tk;
+                if (gi >= 0 && gi < n && gj >= 0 && gj < n && gk >= 0 && gk < n) {
+                    const long long idx = (gi * n + gj) * n + gk;
+                    red_add(image + npl + idx, w);
+                    red_add(image + idx, q);
+                }
+            }
+        }
+        __syncthreads();   // tile and s_work are reused
+    }
+    touched = (unsigned long long)warp_sum_ll((long long)touched);
+    if (lane == 0) {
+        if (touched) atomicAdd(&counters[CNT_TOUCHED], touched);
+        if (fallback) atomicAdd(&counters[CNT_FALLBACK], fallback);
+        if (mapped) atomicAdd(&counters[CNT_MAPPED], mapped);
+        if (mapped) atomicAdd(&counters[CNT_SCATTER], mapped);
+        if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
+    }
+}
+
+template <int KID>
+static int launch_scatter3d_tile_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list,
+                                   long long n_list, double* image)
+{
+    const int nb8 = (int)((G.npix + B3 - 1) / B3);
+    const long long nkeys_ll = (long long)nb8 * nb8 * nb8;
+    const int nkeys = (int)nkeys_ll;
+    void *d_k, *d_k2, *d_i, *d_i2, *d_tmp, *d_beg, *d_end, *d_nch, *d_cb;
+    S2G_TRY(s2g_scratch(ctx, "o3_keys", sizeof(unsigned) * n_list, &d_k));
+    S2G_TRY(s2g_scratch(ctx, "o3_keys2", sizeof(unsigned) * n_list, &d_k2));
+    S2G_TRY(s2g_scratch(ctx, "o3_idx", sizeof(unsigned) * n_list, &d_i));
+    S2G_TRY(s2g_scratch(ctx, "o3_idx2", sizeof(unsigned) * n_list, &d_i2));
+    S2G_TRY(s2g_scratch(ctx, "t3_beg", sizeof(unsigned) * (nkeys + 1), &d_beg));
+    S2G_TRY(s2g_scratch(ctx, "t3_end", sizeof(unsigned) * (nkeys + 1), &d_end));
+    S2G_TRY(s2g_scratch(ctx, "t3_nch", sizeof(unsigned) * (nkeys + 1), &d_nch));
+    S2G_TRY(s2g_scratch(ctx, "t3_cb", sizeof(unsigned) * (nkeys + 1), &d_cb));
+    cudaStream_t st = ctx->stream;
+    const int phs = s2g_phase_begin(ctx, PH_SORT);
+    k_tile3_keys<<<(int)((n_list + 255) / 256), 256, 0, st>>>(P, G, reinterpret_cast<const unsigned*>(list), n_list, nb8,
+                                                              (unsigned*)d_k, (unsigned*)d_i);
+    S2G_CUDA(cudaGetLastError());
+    int bits = 1;
+    while ((1LL << bits) < nkeys_ll) ++bits;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                    (unsigned*)d_i2, (int)n_list, 0, bits, st);
+    S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
+    S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                             (unsigned*)d_i2, (int)n_list, 0, bits, st));
+    S2G_CUDA(cudaMemsetAsync(d_beg, 0, sizeof(unsigned) * (nkeys + 1), st));
+    S2G_CUDA(cudaMemsetAsync(d_end, 0, sizeof(unsigned) * (nkeys + 1), st));
+    S2G_CUDA(cudaMemsetAsync(d_nch, 0, sizeof(unsigned) * (nkeys + 1), st));
+    k_tile3_bounds<<<(int)((n_list + 255) / 256), 256, 0, st>>>((const unsigned*)d_k2, n_list, (unsigned*)d_beg,
+                                                                (unsigned*)d_end);
+    S2G_CUDA(cudaGetLastError());
+    k_tile3_chunks<<<(nkeys + 255) / 256, 256, 0, st>>>((const unsigned*)d_beg, (const unsigned*)d_end, nkeys,
+                                                        (unsigned*)d_nch);
+    S2G_CUDA(cudaGetLastError());
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const unsigned*)d_nch, (unsigned*)d_cb, nkeys + 1, st);
+    S2G_TRY(s2g_scratch(ctx, "g_tmp", tb + 16, &d_tmp));
+    S2G_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, (const unsigned*)d_nch, (unsigned*)d_cb, nkeys + 1, st));
+    unsigned h_chunks = 0;
+    s2g_readback rb(ctx);
+    S2G_CUDA(rb.add(&h_chunks, (unsigned*)d_cb + nkeys, sizeof(unsigned)));
+    s2g_phase_end(ctx, phs);
+    S2G_CUDA(rb.sync());
+    ctx->launches += 7;
+    if (h_chunks == 0) return S2G_OK;
+    const size_t smem = sizeof(double) * 2 * T3 * T3 * T3;
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        S2G_CUDA(cudaFuncSetAttribute(k_scatter3d_tile<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), st));
+    const int blocks = (int)std::min<long long>((long long)h_chunks, (long long)ctx->sm_count);
+    const int ph = s2g_phase_begin(ctx, PH_DEPOSIT);
+    k_scatter3d_tile<KID><<<std::max(blocks, 1), TILE_THREADS, smem, st>>>(
+        P, G, (const unsigned*)d_i2, (const unsigned*)d_beg, (const unsigned*)d_end, (const unsigned*)d_cb, nkeys, nb8,
+        h_chunks, image, ctx->d_counters);
+    s2g_phase_end(ctx, ph);
+    S2G_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return S2G_OK;
 }
 
 // coarse spatial key of a particle: the 16^3-cell block holding its centre.  Particles are DEPOSITED in key order so
@@ -285,6 +511,13 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
                               double* image)
 {
     if (n_list <= 0) return S2G_OK;
+    // shared-memory tile path (S2G_3D_TILE=0: off): needs enough particles per 8^3 block to pay for the tile flushes
+    const char* e_t = getenv("S2G_3D_TILE");
+    const bool tile_on = e_t ? atoi(e_t) != 0 : true;
+    const long long nb8 = (G.npix + B3 - 1) / B3;
+    if (tile_on && n_list >= 32768 && G.npix >= T3 && nb8 * nb8 * nb8 < (1LL << 31) &&
+        n_list * 64 >= nb8 * nb8 * nb8)   // on average at least 1/64 particle per block, else the flushes dominate
+        return launch_scatter3d_tile_k<KID>(ctx, P, G, list, n_list, image);
     const unsigned* order = reinterpret_cast<const unsigned*>(list);
     const char* e_ord = getenv("S2G_3D_ORDER");
     if (!list && (e_ord ? atoi(e_ord) != 0 : true) && P.n >= 65536) {
