@@ -511,9 +511,12 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
                               double* image)
 {
     if (n_list <= 0) return S2G_OK;
-    // shared-memory tile path (S2G_3D_TILE=0: off): needs enough particles per 8^3 block to pay for the tile flushes
+    // shared-memory tile path: OFF by default (S2G_3D_TILE=1 switches it on).  Measured on C3 (profiles/
+    // r2_3d_experiments.txt): 2470 ms per step with the default 8 Mi slices, 1437 ms with one 64 Mi slice, against
+    // 1010 ms for the red.global path — a shared-memory FP64 atomicAdd costs the SM issue slots (the kernel is bound by
+    // its instruction stream), while red.global is one fire-and-forget instruction whose work is done by the L2.
     const char* e_t = getenv("S2G_3D_TILE");
-    const bool tile_on = e_t ? atoi(e_t) != 0 : true;
+    const bool tile_on = e_t ? atoi(e_t) != 0 : false;
     const long long nb8 = (G.npix + B3 - 1) / B3;
     if (tile_on && n_list >= 32768 && G.npix >= T3 && nb8 * nb8 * nb8 < (1LL << 31) &&
         n_list * 64 >= nb8 * nb8 * nb8)   // on average at least 1/64 particle per block, else the flushes dominate
