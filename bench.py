@@ -507,7 +507,7 @@ def run_workload(e, name, steps, warmup, main):
         lp = live_peaks(e)
         hbm_peak = float(pk.get("hbm_gbs", 6650.0))
         dep_ms = st["ms_deposit"] if st["ms_deposit"] > 0 else ms_step
-        strategy_gather = dims == 2 and st["n_pairs"] > 0
+        strategy_gather = dims == 2 and st["n_pairs"] > 0 and st["n_gather"] >= st["n_scatter"]
         hp_gather = healpix and st["n_pairs"] > 0
         kernel_name = ("k_stencil" if stencil else
                        {2: "k_gather2d" if strategy_gather else "k_scatter2d", 3: "k_scatter3d",
