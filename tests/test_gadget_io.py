@@ -126,3 +126,32 @@ def test_distributed_cic_map_from_subfiles(s2g, oracle, tmp_path):
     assert_parity(img, ref, 1e-10, "distributed_cic_map over sub-files")
     back, rpar, snap, units = s2g.read_fits_image(out)
     assert snap == 11 and units == "erg" and np.array_equal(back, img[:, :, 0])
+
+
+def test_block_markers_are_unsigned_and_wrap_modulo_4gib(tmp_path):
+    """record markers are unsigned 32-bit; a block of >= 4 GiB wraps.  A sparse file with a 4 GiB + 24 B
+    'POS ' payload (marker 24) followed by a small 'ID  ' block must scan to the right offsets and sizes."""
+    import struct
+    from sphtogrid_b200 import gadget
+    path = tmp_path / "snap_big"
+    big = (1 << 32) + 24
+    try:
+        with open(path, "wb") as f:
+            def label(name, payload_len):
+                f.write(struct.pack("<I4sII", 8, name, (payload_len + 8) % (1 << 32), 8))
+            label(b"HEAD", 256)
+            f.write(struct.pack("<I", 256)); f.write(b"\0" * 256); f.write(struct.pack("<I", 256))
+            label(b"POS ", big)
+            f.write(struct.pack("<I", big % (1 << 32)))
+            f.seek(big, 1)                                   # sparse payload
+            f.write(struct.pack("<I", big % (1 << 32)))
+            label(b"ID  ", 16)
+            f.write(struct.pack("<I", 16)); f.write(b"\1" * 16); f.write(struct.pack("<I", 16))
+    except OSError as e:
+        pytest.skip(f"cannot create a sparse 4 GiB file here: {e}")
+    with open(path, "rb") as f:
+        blocks = gadget._scan_blocks(f)
+    assert blocks["HEAD"] == (20, 256)
+    pos_off = 20 + 256 + 4 + 16 + 4
+    assert blocks["POS"] == (pos_off, big)
+    assert blocks["ID"] == (pos_off + big + 4 + 16 + 4, 16)

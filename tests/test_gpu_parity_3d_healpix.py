@@ -361,3 +361,30 @@ def test_healpix_tile_gather_slices(s2g, oracle, monkeypatch):
                 assert st[k] == ref[2][k], (k, batch, cap)
             assert_parity(wm, ref[1], rtol=1e-12, what=f"slices {batch}/{cap}")
             assert_parity(a, ref[0], rtol=1e-12, what=f"slices {batch}/{cap}")
+
+
+def test_healpix_map_strict_reference_opt_out(s2g, oracle):
+    """`strict_reference=False` maps exactly the particles inside the shell (with Bin_q > 0 when
+    calc_mean=False) instead of reproducing the reference's sorted[mask] / BoundsError quirks."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    center = np.array([1.0, 2.0, -1.0])
+    pos = rng.normal(size=(n, 3)) * 40.0 + center
+    hsml = rng.random(n) * 3.0 + 0.5
+    m = rng.random(n) + 0.5; rho = rng.random(n) + 0.5; q = rng.random(n) * 10; w = rng.random(n) + 0.5
+    q[::5] = 0.0
+    rl = [20.0, 60.0]
+    for calc_mean in (True, False):
+        p1 = pos.copy()
+        a, wm = s2g.healpix_map(p1, hsml, m, rho, q, w, center=center, radius_limits=rl, Nside=64,
+                                kernel=s2g.WendlandC4(2), show_progress=False, calc_mean=calc_mean,
+                                strict_reference=False)
+        assert np.array_equal(p1, pos - center)
+        d = pos - center
+        r = np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2 + d[:, 2] ** 2)
+        keep = (r >= rl[0]) & (r <= rl[1])
+        if not calc_mean:
+            keep &= q > 0
+        ea, ew, est = oracle.healpix_deposit(d[keep], hsml[keep], m[keep], rho[keep], q[keep], w[keep], 64, "WendlandC4",
+                                             2, calc_mean, n_workers=ncores(), exact="sens")
+        assert_healpix_parity(a, wm, ea, ew, est, what=f"strict_reference=False calc_mean={calc_mean}")
