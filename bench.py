@@ -374,20 +374,24 @@ def run_workload(e, name, steps, warmup, main):
     xwork = {}
     divide = sdist.device_divide(ctx)
 
+    def exchange_only():
+        if healpix or stencil:
+            dist.reduce(image, dst=0)
+            return
+        flat = sdist.exchange_reduce(image, 1, ncell, dims, True, divide, work=xwork, gather="root")
+        if rank == 0:
+            if dims == 2:
+                _lib.check(L.s2g_reduce_image_2d_dev(ctx.handle, P(flat), npix, npix, 1, 0, P(out)))
+            else:
+                out.copy_(flat)
+
     def step_device():
         deposit_only()
         if world > 1:
-            # image = sum(fetch.(futures)) (cic_interpolation.jl:199): the one exchange step of the path
-            if healpix or stencil:
-                dist.reduce(image, dst=0)                       # un-reduced maps go back to the master
-                return
-            # reduce-scatter per plane, reduce_image division on this rank's pixel slice, gather on the master
-            flat = sdist.exchange_reduce(image, 1, ncell, dims, True, divide, work=xwork, gather="root")
-            if rank == 0:
-                if dims == 2:   # transposition to Array(N,N,1) memory (reduce_image = 0: the division is done)
-                    _lib.check(L.s2g_reduce_image_2d_dev(ctx.handle, P(flat), npix, npix, 1, 0, P(out)))
-                else:
-                    out.copy_(flat)
+            # image = sum(fetch.(futures)) (cic_interpolation.jl:199): the one exchange step of the path — un-reduced
+            # HEALPix / stencil maps are reduced to the master; 2D / 3D: reduce-scatter per plane, reduce_image division
+            # on this rank's pixel slice, gather on the master, transposition to Array(N,N,1) memory
+            exchange_only()
             return
         if healpix or stencil:
             return
@@ -425,6 +429,19 @@ def run_workload(e, name, steps, warmup, main):
 
     sampler = ClockSampler(e.local_rank) if (rank == 0 and main) else None
     ms_step, wall_step = timed(step_device, steps, warmup, sampler)
+    # the exchange step alone (N > 1): device time of reduce-scatter + slice division + gather + transposition
+    exchange_ms = None
+    if world > 1:
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        for _ in range(3):
+            exchange_only()
+        x1.record(stream)
+        barrier()
+        tx = torch.tensor([x0.elapsed_time(x1) / 3.0], dtype=f64, device=dev)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        exchange_ms = float(tx[0])
     # counters and phase times of one more deposit (the last library call of a step is the reduce)
     deposit_only()
     st = ctx.stats()
@@ -585,6 +602,7 @@ def run_workload(e, name, steps, warmup, main):
                                           "reduce(NCCL) of the two un-reduced maps to rank 0" if (healpix or stencil) else
                                           "reduce_scatter(NCCL) per plane + reduce_image division of the rank's pixel "
                                           "slice + gather on rank 0 + transposition"),
+                             "exchange_ms": exchange_ms,
                              "shard": "domain_decomposition by particle id (uniform synthetic stream); work imbalance "
                                       "max/mean - 1 = %.4f" % imb},
                   "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches * steps,
