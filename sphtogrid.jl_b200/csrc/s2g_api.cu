@@ -439,6 +439,10 @@ static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, cons
         // helper thread: chunks of 1 Mi particles, all six arrays of a chunk, then the chunk's event
         if (!ctx->stager) {
             ctx->stager = new s2g_stager();
+            if (const char* e = getenv("S2G_STAGE_CHUNK")) {
+                const long long c = atoll(e);
+                if (c >= 65536) ctx->stager->chunk = c;
+            }
             S2G_CUDA(cudaStreamCreateWithFlags(&ctx->stager->copy_stream, cudaStreamNonBlocking));
             S2G_CUDA(cudaEventCreateWithFlags(&ctx->stager->start_ev, cudaEventDisableTiming));
         }
