@@ -381,15 +381,10 @@ int deposit3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, double*
     cudaStream_t st = ctx->stream;
     long long p0 = 0;
     long long batch = std::min(batch_max, (long long)P.n);
-    long long ramp = std::max<long long>(s2g_stage_first_slice(ctx), 1);
     while (p0 < P.n) {
         long long nb = std::min(batch, (long long)P.n - p0);
         // overlapped staging (s2g_api.cu): small first slice, every slice waits for exactly the particles it reads
-        // (slices of 1, 2, 4, ... chunks: a 3D slice computes for less time than the next 8 Mi particles take to copy)
-        if (s2g_stage_first_slice(ctx) > 0 && ramp < batch) {
-            nb = std::min(nb, ramp);
-            ramp *= 2;
-        }
+        if (p0 == 0 && s2g_stage_first_slice(ctx) > 0) nb = std::min(nb, s2g_stage_first_slice(ctx));
         S2G_TRY(s2g_stage_wait(ctx, p0 + nb));
         void *d_cls, *d_np, *d_ps, *d_pg, *d_ls, *d_lg, *d_tmp, *d_sum;
         S2G_TRY(s2g_scratch(ctx, "g_cls", sizeof(int) * (nb + 1), &d_cls));

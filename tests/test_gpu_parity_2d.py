@@ -297,3 +297,42 @@ def test_map_it_like_the_precompile_workload(s2g, oracle, tmp_path):
         assert_parity(m, ref, what="map_it " + kname)
         d, _, _, units = s2g.read_fits_image(str(tmp_path / "dummy") + ".xy.fits")
         assert np.array_equal(d, m[:, :, 0]) and units == "T"
+
+
+@pytest.mark.parametrize("bounce", ["1", "0"])
+def test_overlapped_staging_path(s2g, oracle, bounce, monkeypatch):
+    """The host-array entry points copy large inputs on a helper thread, chunk by chunk, while the sliced deposit runs
+    (s2g_stage_wait per slice; csrc/s2g_api.cu).  The thresholds are lowered so that a 60 k-particle call goes through
+    that machinery — many chunks, many slices, through own pinned bounce buffers (default) or the driver's pageable path —
+    and must give the map of the plain path: 2D (gather + scatter bins), 3D and HEALPix."""
+    monkeypatch.setenv("S2G_STAGE_MIN", "1000")
+    monkeypatch.setenv("S2G_STAGE_CHUNK", "4096")
+    monkeypatch.setenv("S2G_BATCH_PARTICLES", "10000")
+    monkeypatch.setenv("S2G_STAGE_BOUNCE", bounce)
+    ctx = s2g.Context(0)          # a fresh context: the staging thread and its buffers are created with these settings
+    pos, hsml, m, rho, q, w = random_particles(61, 60000, box=6.5, hmin=0.01, hmax=0.5, center=3.0)
+    hsml[:3000] *= 4.0
+    kw = dict(center=[3.0, 3.0, 3.0], x_size=5.4, y_size=5.4, z_size=5.4, Npixels=192, boxsize=6.0)
+    for it in range(2):           # twice: buffers and events are reused by the second call
+        p1, p2 = pos.copy(), pos.copy()
+        got, st = s2g.sphMapping(p1, hsml, m, rho, q, w, param=s2g.mappingParameters(**kw), kernel=s2g.WendlandC6(2),
+                                 calc_mean=True, show_progress=False, ctx=ctx, return_stats=True)
+        ref = oracle.sph_mapping(p2, hsml, m, rho, q, w, param=oracle.mapping_parameters(**kw), kernel="WendlandC6",
+                                 calc_mean=True)
+        assert np.array_equal(p1, p2)
+        assert st["n_gather"] > 0 and st["n_scatter"] > 0
+        assert_parity(got, ref, what=f"staged 2D, call {it}")
+    kw3 = dict(kw, Npixels=40)
+    got = s2g.sphMapping(pos.copy(), hsml, m, rho, q, w, param=s2g.mappingParameters(**kw3), kernel=s2g.Cubic(3),
+                         dimensions=3, show_progress=False, ctx=ctx)
+    ref = oracle.sph_mapping(pos.copy(), hsml, m, rho, q, w, param=oracle.mapping_parameters(**kw3), kernel="Cubic",
+                             dimensions=3)
+    assert_parity(got, ref, what="staged 3D")
+    hp = pos - 3.0
+    a, wm = s2g.healpix_map(hp.copy(), hsml, m, rho, q, w, center=[0.1, -0.2, 0.05], Nside=64, kernel=s2g.WendlandC4(2),
+                            show_progress=False, ctx=ctx)
+    ea, ew, est = oracle.healpix_map(hp.copy(), hsml, m, rho, q, w, center=[0.1, -0.2, 0.05], nside=64, kernel="WendlandC4",
+                                     exact="sens", n_workers=4)
+    from util import assert_healpix_parity
+    assert_healpix_parity(a, wm, ea, ew, est, what="staged HEALPix")
+    ctx.close()
