@@ -62,7 +62,8 @@ __constant__ double kG[8] = {1.0,
                              135135.0 / 9676800.0 / 16384.0};
 
 // ---- classification: which path deposits particle p
-//   heavy[p]      very large disc the gather cannot take (over a pole, ...) -> cooperative scatter launch
+//   heavy[p]      very large disc the gather cannot take (non-finite quantity or normalisation, >= 1.5 rad)
+//                 -> cooperative scatter launch
 //   gath[p]       disc for the tile-gather: 1 = below 0.073 rad (short series), 2 = up to 0.2 rad
 //   gath_heavy[p] disc above 0.2 rad for the tile-gather (asin instead of its series)
 //   skip[p] = 1   the ordinary scatter launch must NOT take it (any of the three above)
@@ -86,11 +87,9 @@ __global__ void __launch_bounds__(256) k_hp_classify(s2g_particles P, HpGeom g, 
         h = (heavy_radius > 0.0 && hs >= dx * sin(heavy_radius)) ? 1 : 0;
         if (gather_on) {
             const double ph = asin(__ddiv_rn(hs, dx));
-            const double theta = acos(__ddiv_rn(z, dx));
             const double m = 2.0 * g.ang_pix;
             const double an_probe = ld_in(P.m, p, P.in_dtype) / ld_in(P.rho, p, P.in_dtype) * ld_in(P.w, p, P.in_dtype);
-            const bool ok = ph >= gather_radius && ph < 1.5 && theta - ph > m && theta + ph < kPi - m && isfinite(q) &&
-                            isfinite(an_probe) && an_probe != 0.0;
+            const bool ok = ph >= gather_radius && ph < 1.5 && isfinite(q) && isfinite(an_probe) && an_probe != 0.0;
             if (ok) {
                 // ga = 1: small-angle disc (5 series coefficients are exact to 1e-16 below 0.073 rad), 2: up to 0.2 rad
                 // (8 coefficients); gh: above — asin itself (BIG instantiation, 2 CTAs/SM)
@@ -145,9 +144,12 @@ __global__ void __launch_bounds__(256) k_hp_records(s2g_particles P, HpGeom g, c
     // the two (ang_pix Δx)² cancel, pix_weight = (area·w·dz / Σ wk·A')·wk·A'
     r.an = area * ld_in(P.w, p, P.in_dtype) * dz;
     r.anq = ld_in(P.binq, p, P.in_dtype);          // the quantity; becomes an*q in k_hp_normalise
-    const bool ok = !d.full_sky && d.ring_first == d.irmin && d.ring_last == d.irmax && d.irmin <= d.irmax;
-    r.rmin = ok ? (int)d.irmin : 1;
-    r.rmax = ok ? (int)d.irmax : 0;
+    // all rings of the walk: the disc's rings [irmin, irmax] plus, when a pole lies inside the disc, the whole rings
+    // between that pole and the disc's first / last ring (query_disc appends them entirely; they are geometrically
+    // inside the disc, so the gather's membership test agrees)
+    const bool ok = !d.full_sky && d.ring_first <= d.ring_last;
+    r.rmin = ok ? (int)d.ring_first : 1;
+    r.rmax = ok ? (int)d.ring_last : 0;
     r.ntot = 0;
     r.pad = (int)p;
     recs[t] = r;
@@ -219,8 +221,7 @@ __global__ void __launch_bounds__(256) k_hp_pairs(HRec* __restrict__ recs, long 
     d.Dx = 1.0;
     d.proj_h = r.ph;
     d.hinv = 1.0 / r.ph;
-    make_disc(g, d);
-    d.irmin = r.rmin; d.irmax = r.rmax;      // the ring range of pass A (computed from the unrounded position)
+    make_disc(g, d);   // (from the unit vector: its ring range may differ from the record's by a ring that barely touches)
     const int b0 = (r.rmin - 1) / HPG_BR, b1 = (r.rmax - 1) / HPG_BR;
     unsigned count = 0;
     unsigned o = WRITE ? off[t] : 0u;
