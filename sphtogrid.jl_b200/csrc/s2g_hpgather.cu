@@ -111,11 +111,6 @@ struct HpTiles {
     const int* band_ns;    // [nbands]   sectors of a band
 };
 
-__device__ __forceinline__ long long ring_len(const HpGeom& g, long long ring)
-{
-    return ring < g.nside ? 4 * ring : (ring <= 3 * g.nside ? g.nl4 : 4 * (g.nl4 - ring));
-}
-
 // ---- records without a ring walk: everything of main.jl:143-193 that does not need the pixel list.  `an` holds the
 // UN-normalised area·w·dz/(ang_pix Δx)² until k_hp_normalise divides it by Σ wk·A' (pass A as a tile-gather, below):
 // area_norm = kernel_norm·wpp·w·dz = (area/N)(N/Σ)·w·dz, N cancels (main.jl:32-33, pixel_weights.jl:119-137).
