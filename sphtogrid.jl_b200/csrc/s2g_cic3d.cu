@@ -19,7 +19,8 @@
 #define S2G_3D_CAP 1024
 #endif
 #ifndef S2G_3D_MINB
-#define S2G_3D_MINB 1     // min CTAs/SM of k_scatter3d (register cap): -DS2G_3D_MINB=3 -DS2G_3D_CAP=640 is the A/B variant
+#define S2G_3D_MINB 2     // min CTAs/SM of k_scatter3d: 128 registers, no spills (uncapped the compiler has taken 137 -> ONE
+                          // CTA per SM); -DS2G_3D_MINB=3 -DS2G_3D_CAP=640 is the measured-slower A/B variant
 #endif
 constexpr int S3_CAP = S2G_3D_CAP;
 
@@ -72,7 +73,11 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
     // the list compaction can ballot
     double sw = 0.0;
     int cnt = 0;
-    bool cache = (s_w != nullptr) && ni < 256 && nj < 256 && nk < 256;
+    // list entries: TILE keeps the box coordinates (8 bits each), the red path the cell's linear offset from the box
+    // corner (32 bits: ni n^2 < 2^32), so that pass B is one widening multiply-add per plane
+    const unsigned nn1 = (unsigned)G.npix, nn2 = nn1 * nn1;
+    bool cache = (s_w != nullptr) &&
+                 (TILE ? (ni < 256 && nj < 256 && nk < 256) : ((long long)ni * G.npix * G.npix < (1LL << 32)));
     int n_list = 0;                 // uniform
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int kb = 0; kb < nk; kb += W) {
@@ -89,10 +94,12 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
             if (!__any_sync(0xffffffffu, colv)) continue;
             const double dy = (j == r.lo[1]) ? dy_lo : ((j == r.hi[1]) ? dy_hi : 1.0);
             const double dydz = dy * dz;
+            const unsigned colo = TILE ? (((unsigned)jr << 8) | (unsigned)kc) : ((unsigned)jr * nn1 + (unsigned)kc);
             double col = 0.0;
             for (int ii = 0; ii < ni; ii += 4) {
                 double wk[4];
                 bool in[4];
+#pragma unroll
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const double a = fma(-(double)(ii + q), hinv, xb);
@@ -114,7 +121,7 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                         const int pos = n_list + __popc(m & lt_mask);
                         if (live && pos < S3_CAP) {
                             s_w[pos] = gq;
-                            s_c[pos] = ((unsigned)(ii + q) << 16) | ((unsigned)jr << 8) | (unsigned)kc;
+                            s_c[pos] = TILE ? (((unsigned)(ii + q) << 16) | colo) : ((unsigned)(ii + q) * nn2 + colo);
                         }
                         n_list += __popc(m);
                     }
@@ -191,6 +198,8 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
         if (!live_p) return;
         __syncwarp();
         const long long o0 = (long long)r.lo[0] * n * n + (long long)r.lo[1] * n + r.lo[2];
+        double* __restrict__ img_q = image + o0;
+        double* __restrict__ img_w = image + npl + o0;
         for (int t = lane; t < n_list; t += 32) {
             const double g = s_w[t];
             const unsigned c = s_c[t];
@@ -198,9 +207,8 @@ __device__ __forceinline__ void warp_deposit_3d(const Rec3& r, const s2g_geom& G
                 deposit_cell<true>(sk, image, npl, n, r.lo[0] + (int)(c >> 16), r.lo[1] + (int)((c >> 8) & 255u),
                                    r.lo[2] + (int)(c & 255u), g * volume_norm, g * vq);
             else {
-                const long long idx = o0 + (long long)(c >> 16) * n * n + (long long)((c >> 8) & 255u) * n + (c & 255u);
-                red_add(image + npl + idx, g * volume_norm);
-                red_add(image + idx, g * vq);
+                red_add(img_w + c, g * volume_norm);
+                red_add(img_q + c, g * vq);
             }
         }
         if (lane == 0) touched += (unsigned long long)n_list;
@@ -488,11 +496,13 @@ static int launch_scatter3d_tile_k(s2g_ctx* ctx, const s2g_particles& P, const s
 // coarse spatial key of a particle: the 16^3-cell block holding its centre.  Particles are DEPOSITED in key order so
 // that the ~2400 particles in flight update a compact region of the grid: with random order every red row misses L2
 // (measured 474 GB of DRAM traffic for 2·10^10 reds on the c3s sample).
-__global__ void __launch_bounds__(256) k_order3d_keys(s2g_particles P, s2g_geom G, unsigned* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_order3d_keys(s2g_particles P, s2g_geom G, const int* __restrict__ list,
+                                                      long long n_list, unsigned* __restrict__ keys,
                                                       unsigned* __restrict__ idx)
 {
-    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_list) return;
+    const long long p = list ? (long long)list[t] : t;
     const int nb = (int)((G.npix + 15) / 16);
     unsigned key = 0;
 #pragma unroll
@@ -502,8 +512,8 @@ __global__ void __launch_bounds__(256) k_order3d_keys(s2g_particles P, s2g_geom 
         b = min(max(b, 0), nb - 1);
         key = key * (unsigned)nb + (unsigned)b;
     }
-    keys[p] = key;
-    idx[p] = (unsigned)p;
+    keys[t] = key;
+    idx[t] = (unsigned)p;
 }
 
 template <int KID>
@@ -523,24 +533,26 @@ static int launch_scatter3d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
         return launch_scatter3d_tile_k<KID>(ctx, P, G, list, n_list, image);
     const unsigned* order = reinterpret_cast<const unsigned*>(list);
     const char* e_ord = getenv("S2G_3D_ORDER");
-    if (!list && (e_ord ? atoi(e_ord) != 0 : true) && P.n >= 65536) {
+    // the class list of the AUTO strategy (list != nullptr) is in input order: it is put in key order like the whole set
+    if ((e_ord ? atoi(e_ord) != 0 : true) && n_list >= 65536 && n_list < (1LL << 31)) {
         void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
-        S2G_TRY(s2g_scratch(ctx, "o3_keys", sizeof(unsigned) * P.n, &d_k));
-        S2G_TRY(s2g_scratch(ctx, "o3_keys2", sizeof(unsigned) * P.n, &d_k2));
-        S2G_TRY(s2g_scratch(ctx, "o3_idx", sizeof(unsigned) * P.n, &d_i));
-        S2G_TRY(s2g_scratch(ctx, "o3_idx2", sizeof(unsigned) * P.n, &d_i2));
+        S2G_TRY(s2g_scratch(ctx, "o3_keys", sizeof(unsigned) * n_list, &d_k));
+        S2G_TRY(s2g_scratch(ctx, "o3_keys2", sizeof(unsigned) * n_list, &d_k2));
+        S2G_TRY(s2g_scratch(ctx, "o3_idx", sizeof(unsigned) * n_list, &d_i));
+        S2G_TRY(s2g_scratch(ctx, "o3_idx2", sizeof(unsigned) * n_list, &d_i2));
         const int phs = s2g_phase_begin(ctx, PH_SORT);
-        k_order3d_keys<<<(int)((P.n + 255) / 256), 256, 0, ctx->stream>>>(P, G, (unsigned*)d_k, (unsigned*)d_i);
+        k_order3d_keys<<<(int)((n_list + 255) / 256), 256, 0, ctx->stream>>>(P, G, list, n_list, (unsigned*)d_k,
+                                                                               (unsigned*)d_i);
         S2G_CUDA(cudaGetLastError());
         const int nb = (int)((G.npix + 15) / 16);
         int bits = 1;
         while ((1LL << bits) < (long long)nb * nb * nb) ++bits;
         size_t sb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
-                                        (unsigned*)d_i2, (int)P.n, 0, bits, ctx->stream);
+                                        (unsigned*)d_i2, (int)n_list, 0, bits, ctx->stream);
         S2G_TRY(s2g_scratch(ctx, "g_sort_tmp", sb + 16, &d_tmp));
         S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
-                                                 (unsigned*)d_i2, (int)P.n, 0, bits, ctx->stream));
+                                                 (unsigned*)d_i2, (int)n_list, 0, bits, ctx->stream));
         s2g_phase_end(ctx, phs);
         ctx->launches += 4;
         order = (const unsigned*)d_i2;

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) k_hpg_tile_chunks(const unsigned* __restr
 // NT: coefficients of G(c2) = asin(x)/x kept (8: exact to 1e-16 up to 0.2 rad; 5: up to 0.073 rad, the bulk of a survey
 // volume — a compile-time constant: choosing it per record inside the loop cost more than it saved).
 template <int KID, bool BIG, bool PASSA, int NT>
-__global__ void __launch_bounds__(HPG_THREADS, BIG ? 2 : HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
+__global__ void __launch_bounds__(HPG_THREADS, (BIG && !PASSA) ? 2 : HPG_CTAS) k_hp_gather(const HRec* __restrict__ recs,
                                                                      const unsigned* __restrict__ vals,
                                                                      const unsigned* __restrict__ tile_beg,
                                                                      const unsigned* __restrict__ tile_end,
@@ -554,7 +554,7 @@ int launch_gather_k(s2g_ctx* ctx, const HRec* recs, const unsigned* vals, const 
                     int big, double* Ssum, int nt)
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
-    const int blocks = std::max((int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * (big ? 2 : HPG_CTAS)), 1);
+    const int blocks = std::max((int)std::min<long long>((long long)chunks, (long long)ctx->sm_count * ((big && !Ssum) ? 2 : HPG_CTAS)), 1);   // asin + deposit: 100 registers
 #define HPG_LAUNCH(B, A, N) k_hp_gather<KID, B, A, N><<<blocks, HPG_THREADS, 0, ctx->stream>>>(recs, vals, tbeg, tend, cbeg, g, T, \
                                                                                                chunks, amap, wmap, ctx->d_counters, Ssum)
     if (Ssum) { if (big) HPG_LAUNCH(true, true, 8); else if (nt >= 8) HPG_LAUNCH(false, true, 8); else HPG_LAUNCH(false, true, 5); }
