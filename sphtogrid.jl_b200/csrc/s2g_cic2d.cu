@@ -4,6 +4,9 @@
 // Replaces: cic_mapping_2D (src/cic_interpolation/cic_2D.jl:103-244), calculate_weights (:11-72),
 //           reduce_image_2D (src/cic_interpolation/reduce_image.jl:8-31),
 //           center_particles / filter_particles_in_image (src/cic_interpolation/filter_shift.jl:6-67).
+#include <cub/cub.cuh>
+#include <cstdlib>
+
 #include "s2g_cic2d.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -11,6 +14,109 @@
 // lanes are laid out W wide along j (the contiguous image axis, indices.jl:6-8) and 32/W rows deep,
 // W = next power of two >= footprint width (capped at 32) so that small footprints still fill the warp.
 // ------------------------------------------------------------------------------------------------
+// (row, column) of the flattened footprint index e (j fastest) without an integer division: float reciprocal + one
+// correction step (exact for every e, nj < 2^20)
+__device__ __forceinline__ void unflatten(int e, int nj, float inv_nj, int& ir, int& jc)
+{
+    ir = __float2int_rd(((float)e + 0.5f) * inv_nj);
+    jc = e - ir * nj;
+    if (jc < 0) { --ir; jc += nj; }
+    else if (jc >= nj) { ++ir; jc -= nj; }
+}
+
+// The records of the (up to) 32 particles a warp has taken, one slot per lane, in shared memory: the lane that built a
+// record posts it, every lane reads the slot it is told to (a broadcast when the warp works on one particle).
+struct RecBoard {
+    double d[7][32];
+    int i[6][32];
+};
+__device__ __forceinline__ void board_post(RecBoard& b, int lane, const Rec2& m, long long p)
+{
+    b.d[0][lane] = m.x; b.d[1][lane] = m.y; b.d[2][lane] = m.h; b.d[3][lane] = m.hinv;
+    b.d[4][lane] = m.area; b.d[5][lane] = m.dz; b.d[6][lane] = m.w;
+    b.i[0][lane] = m.iMin; b.i[1][lane] = m.iMax; b.i[2][lane] = m.jMin; b.i[3][lane] = m.jMax;
+    b.i[4][lane] = m.all_zero ? 1 : 0;
+    b.i[5][lane] = (int)p;   // particle indices are below 2^31 (checked at the boundary)
+}
+__device__ __forceinline__ Rec2 board_read(const RecBoard& b, int src, long long& p)
+{
+    Rec2 r;
+    r.x = b.d[0][src]; r.y = b.d[1][src]; r.h = b.d[2][src]; r.hinv = b.d[3][src];
+    r.area = b.d[4][src]; r.dz = b.d[5][src]; r.w = b.d[6][src];
+    r.iMin = b.i[0][src]; r.iMax = b.i[1][src]; r.jMin = b.i[2][src]; r.jMax = b.i[3][src];
+    r.all_zero = b.i[4][src] != 0;
+    p = (long long)b.i[5][src];
+    return r;
+}
+
+constexpr int SC2_CAP = 384;   // pixels of a footprint whose pass-A weights a warp keeps in shared memory (3 KB per warp)
+
+// Footprints of at most SC2_CAP pixels: the warp walks the FLATTENED footprint (all 32 lanes busy whatever the width)
+// and pass A leaves wk dx dy of every pixel in shared memory (a lane reads back only what it wrote: no barrier), so
+// that pass B is one multiply and the reds — no second square root, no second kernel evaluation.  The rare branches
+// (no pixel centre covered, Inf/NaN norm) return false and take the general two-pass code below.
+template <int KID>
+__device__ __forceinline__ bool warp_deposit_2d_cached(const Rec2& r, const s2g_particles& P, const s2g_geom& G, long long p,
+                                                       int lane, double* __restrict__ image, unsigned long long& touched,
+                                                       double* __restrict__ s_g)
+{
+    const int ni = r.iMax - r.iMin + 1, nj = r.jMax - r.jMin + 1, npx = ni * nj;
+    const double dx_lo = overlap_1d(r.x, r.h, r.iMin), dx_hi = overlap_1d(r.x, r.h, r.iMax);
+    const double dy_lo = overlap_1d(r.y, r.h, r.jMin), dy_hi = overlap_1d(r.y, r.h, r.jMax);
+    const float inv_nj = 1.0f / (float)nj;
+    double sw = 0.0;
+    int cnt = 0;
+    for (int e = lane; e < npx; e += 32) {
+        int ir, jc;
+        unflatten(e, nj, inv_nj, ir, jc);
+        const int i = r.iMin + ir, j = r.jMin + jc;
+        const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
+        const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
+        double g = 0.0;
+        if (u <= 1.0) {
+            const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+            const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+            const double wk = kernel_shape<KID>(u);
+            const double dxy = dx * dy;
+            sw = fma(wk, dxy, sw);
+            g = wk * dxy;
+            ++cnt;
+        }
+        s_g[e] = g;
+    }
+    sw = warp_sum(sw);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (sw == 0.0) return false;
+    const double n_distr = (double)cnt, wpp = n_distr / sw;
+    const double kernel_norm = r.area / n_distr;
+    const double area_norm = kernel_norm * wpp * r.w * r.dz;
+    if (!isfinite(area_norm)) return false;
+    const long long npl = G.npix * G.npix;
+    double* __restrict__ wplane = image + npl * G.n_images;
+    const int nim = G.n_images;
+    double q0 = 0.0;
+    if (!r.all_zero && nim == 1) q0 = ld_in(P.binq, p, P.in_dtype);
+    for (int e = lane; e < npx; e += 32) {
+        const double pw = s_g[e] * area_norm;
+        if (pw != 0.0) {
+            int ir, jc;
+            unflatten(e, nj, inv_nj, ir, jc);
+            const long long idx = (long long)(r.iMin + ir) * G.npix + (r.jMin + jc);
+            red_add(wplane + idx, pw);
+            if (r.all_zero) {
+                if (!isfinite(pw)) red_add(image + idx, 0.0 * pw);
+            } else if (nim == 1) {
+                red_add(image + idx, q0 * pw);
+            } else {
+                for (int q = 0; q < nim; ++q)
+                    red_add(image + npl * q + idx, ld_in(P.binq, (long long)nim * p + q, P.in_dtype) * pw);
+            }
+            ++touched;
+        }
+    }
+    return true;
+}
+
 template <int KID>
 __device__ __forceinline__ void warp_deposit_2d(const Rec2& r, const s2g_particles& P, const s2g_geom& G, long long p,
                                                 int lane, double* __restrict__ image, unsigned long long& touched,
@@ -123,28 +229,53 @@ __device__ __forceinline__ void warp_deposit_2d(const Rec2& r, const s2g_particl
 template <int KID>
 __global__ void __launch_bounds__(256) k_scatter2d(s2g_particles P, s2g_geom G, const int* __restrict__ list,
                                                    long long n_list, double* __restrict__ image,
-                                                   unsigned long long* __restrict__ counters)
+                                                   unsigned long long* __restrict__ counters, int chunk)
 {
     const int lane = threadIdx.x & 31;
+    __shared__ double s_cache[8 * SC2_CAP];
+    __shared__ RecBoard s_board[8];
+    double* __restrict__ s_g = s_cache + (threadIdx.x >> 5) * SC2_CAP;
+    RecBoard& board = s_board[threadIdx.x >> 5];
     unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
-    constexpr int CHUNK = 4;
+    // a warp takes `chunk` (<= 32) particles at a time: lane l loads particle base + l and builds its record (one
+    // coalesced load per input array, the three divisions of the record once per particle and 32 particles at a time,
+    // one memory latency per chunk instead of one per particle); the warp then deposits them one after the other, the
+    // record handed round by shuffles.
     for (;;) {
         long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
+        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)chunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_list) break;
-        const long long end = min(base + CHUNK, n_list);
-        for (long long t = base; t < end; ++t) {
-            const long long p = list ? (long long)list[t] : t;
-            Rec2 r;
-            if (!make_rec2(P, G, p, r)) continue;
-            if (lane == 0) {
-                ++mapped;
-                fpx += (unsigned long long)(r.iMax - r.iMin + 1) * (unsigned long long)(r.jMax - r.jMin + 1);
-            }
+        const long long tl = base + lane;
+        Rec2 mine = {};
+        long long pm = 0;
+        bool ok = false;
+        if (lane < chunk && tl < n_list) {
+            pm = list ? (long long)list[tl] : tl;
+            ok = make_rec2(P, G, pm, mine);
+        }
+        __syncwarp();   // the previous chunk's records have been read by every lane
+        if (ok) {
+            ++mapped;
+            fpx += (unsigned long long)(mine.iMax - mine.iMin + 1) * (unsigned long long)(mine.jMax - mine.jMin + 1);
+            board_post(board, lane, mine, pm);
+        }
+        __syncwarp();   // posts before reads
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            long long p;
+            const Rec2 r = board_read(board, src, p);
+            const unsigned long long npx =
+                (unsigned long long)(r.iMax - r.iMin + 1) * (unsigned long long)(r.jMax - r.jMin + 1);
+            if (npx <= (unsigned long long)SC2_CAP && warp_deposit_2d_cached<KID>(r, P, G, p, lane, image, touched, s_g))
+                continue;
             warp_deposit_2d<KID>(r, P, G, p, lane, image, touched, fallback);
         }
     }
+    mapped = (unsigned long long)warp_sum_ll((long long)mapped);
+    fpx = (unsigned long long)warp_sum_ll((long long)fpx);
     touched = (unsigned long long)warp_sum_ll((long long)touched);
     if (lane == 0) {
         if (touched) atomicAdd(&counters[CNT_TOUCHED], touched);
@@ -165,29 +296,44 @@ __global__ void __launch_bounds__(256) k_scatter2d(s2g_particles P, s2g_geom G, 
 template <int KID, int SUB>
 __global__ void __launch_bounds__(256) k_scatter2d_sub(s2g_particles P, s2g_geom G, const int* __restrict__ list,
                                                        long long n_list, double* __restrict__ image,
-                                                       unsigned long long* __restrict__ counters)
+                                                       unsigned long long* __restrict__ counters, int chunk)
 {
     constexpr int GROUPS = 32 / SUB;
-    constexpr int CHUNK = 4 * GROUPS;
     const int lane = threadIdx.x & 31, grp = lane / SUB, sub = lane % SUB;
+    __shared__ double s_cache[8 * 256];
+    __shared__ RecBoard s_board[8];
+    double* __restrict__ s_g = s_cache + (threadIdx.x >> 5) * 256;
+    RecBoard& board = s_board[threadIdx.x >> 5];
     unsigned long long touched = 0, fallback = 0, mapped = 0, fpx = 0;
     const long long npl = G.npix * G.npix;
     double* __restrict__ wplane = image + npl * G.n_images;
     const int nim = G.n_images;
     for (;;) {
         long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)CHUNK);
+        if (lane == 0) base = (long long)atomicAdd(&counters[CNT_WORK], (unsigned long long)chunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_list) break;
-        for (long long t0 = base; t0 < min(base + CHUNK, n_list); t0 += GROUPS) {
-            const long long t = t0 + grp;
+        // lane l loads particle base + l and builds its record (k_scatter2d above); group g then takes the particles
+        // g, g + GROUPS, ... of the chunk
+        const long long tl = base + lane;
+        Rec2 mine = {};
+        long long pm = 0;
+        bool ok = false;
+        if (lane < chunk && tl < n_list) {
+            pm = list ? (long long)list[tl] : tl;
+            ok = make_rec2(P, G, pm, mine);
+        }
+        __syncwarp();   // the previous chunk's records have been read by every lane
+        if (ok) board_post(board, lane, mine, pm);
+        __syncwarp();   // posts before reads
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        for (int k0 = 0; k0 < chunk; k0 += GROUPS) {
+            if (((okmask >> k0) & ((1u << GROUPS) - 1u)) == 0u) continue;   // uniform: nothing to do in this round
+            const int src = min(k0 + grp, 31);
+            const bool act = (k0 + grp < chunk) && ((okmask >> src) & 1u);
             long long p = 0;
-            Rec2 r;
-            bool act = t < n_list;
-            if (act) {
-                p = list ? (long long)list[t] : t;
-                act = make_rec2(P, G, p, r);
-            }
+            Rec2 r = {};
+            if (act) r = board_read(board, src, p);
             int ni = 0, nj = 1, npx = 0;
             double dx_lo = 0, dx_hi = 0, dy_lo = 0, dy_hi = 0;
             if (act) {
@@ -196,20 +342,48 @@ __global__ void __launch_bounds__(256) k_scatter2d_sub(s2g_particles P, s2g_geom
                 dy_lo = overlap_1d(r.y, r.h, r.jMin); dy_hi = overlap_1d(r.y, r.h, r.jMax);
                 if (sub == 0) { ++mapped; fpx += (unsigned long long)npx; }
             }
-            // ---- pass A
+            // ---- pass A.  A footprint of at most SUB x MAXIT = 64 pixels (the tiny class) leaves wk dx dy of the lane's
+            // pixels in shared memory (slot m*32 + lane: a lane reads back only what it wrote), so that pass B neither
+            // takes the square root nor evaluates the kernel a second time; (row, column) of the flattened index come
+            // from a float reciprocal instead of an integer division.
+            constexpr int MAXIT = 64 / SUB;
+            const bool small = npx <= SUB * MAXIT;
+            const float inv_nj = 1.0f / (float)nj;
             double sw = 0.0, da = 0.0;
             int cnt = 0;
-            for (int e = sub; e < npx; e += SUB) {
-                const int ir = e / nj, jc = e - ir * nj;
-                const int i = r.iMin + ir, j = r.jMin + jc;
-                const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
-                const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
-                const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
-                const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
-                da += dx * dy;
-                if (u <= 1.0) {
-                    sw = fma(kernel_shape<KID>(u), dx * dy, sw);
-                    ++cnt;
+            if (small) {
+                for (int e = sub, m = 0; e < npx; e += SUB, ++m) {
+                    int ir, jc;
+                    unflatten(e, nj, inv_nj, ir, jc);
+                    const int i = r.iMin + ir, j = r.jMin + jc;
+                    const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
+                    const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                    const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+                    const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
+                    const double dxy = dx * dy;
+                    da += dxy;
+                    double g = 0.0;
+                    if (u <= 1.0) {
+                        const double wk = kernel_shape<KID>(u);
+                        sw = fma(wk, dxy, sw);
+                        g = wk * dxy;
+                        ++cnt;
+                    }
+                    s_g[m * 32 + lane] = g;
+                }
+            } else {
+                for (int e = sub; e < npx; e += SUB) {
+                    const int ir = e / nj, jc = e - ir * nj;
+                    const int i = r.iMin + ir, j = r.jMin + jc;
+                    const double xd = center_dist(r.x, (double)i), yd = center_dist(r.y, (double)j);
+                    const double dx = (i == r.iMin) ? dx_lo : ((i == r.iMax) ? dx_hi : 1.0);
+                    const double dy = (j == r.jMin) ? dy_lo : ((j == r.jMax) ? dy_hi : 1.0);
+                    const double u = u_of(__dmul_rn(xd, xd), __dmul_rn(yd, yd), r.hinv);
+                    da += dx * dy;
+                    if (u <= 1.0) {
+                        sw = fma(kernel_shape<KID>(u), dx * dy, sw);
+                        ++cnt;
+                    }
                 }
             }
 #pragma unroll
@@ -237,6 +411,27 @@ __global__ void __launch_bounds__(256) k_scatter2d_sub(s2g_particles P, s2g_geom
             double q0 = 0.0;
             if (!r.all_zero && nim == 1) q0 = ld_in(P.binq, p, P.in_dtype);
             // ---- pass B
+            if (small && !fb && !poison) {
+                for (int e = sub, m = 0; e < npx; e += SUB, ++m) {
+                    const double pw = s_g[m * 32 + lane] * area_norm;
+                    if (pw != 0.0) {
+                        int ir, jc;
+                        unflatten(e, nj, inv_nj, ir, jc);
+                        const long long idx = (long long)(r.iMin + ir) * G.npix + (r.jMin + jc);
+                        red_add(wplane + idx, pw);
+                        if (r.all_zero) {
+                            if (!isfinite(pw)) red_add(image + idx, 0.0 * pw);
+                        } else if (nim == 1) {
+                            red_add(image + idx, q0 * pw);
+                        } else {
+                            for (int q = 0; q < nim; ++q)
+                                red_add(image + npl * q + idx, ld_in(P.binq, (long long)nim * p + q, P.in_dtype) * pw);
+                        }
+                        ++touched;
+                    }
+                }
+                continue;
+            }
             for (int e = sub; e < npx; e += SUB) {
                 const int ir = e / nj, jc = e - ir * nj;
                 const int i = r.iMin + ir, j = r.jMin + jc;
@@ -284,16 +479,78 @@ __global__ void __launch_bounds__(256) k_scatter2d_sub(s2g_particles P, s2g_geom
     }
 }
 
+// ---- deposit order of a scatter list: by the 64x64-pixel block of the particle centre.  In input order every red row of
+// a small footprint misses L2 once the image is larger than L2 (read + write of a DRAM sector per row); in block order
+// the ~10^4 particles in flight update one compact region that stays in L2.  One radix sort of (key, index) pairs per
+// list; S2G_2D_ORDER=0 switches it off.
+__global__ void __launch_bounds__(256) k_order2d_keys(s2g_particles P, s2g_geom G, const int* __restrict__ list,
+                                                      long long n_list, int nb, unsigned* __restrict__ keys,
+                                                      unsigned* __restrict__ idx)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_list) return;
+    const long long p = list ? (long long)list[t] : t;
+    unsigned key = 0;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const double x = fma(ld_pos(P, p, d), G.len2pix, G.half_n);
+        int b = (int)floor(x * (1.0 / 64.0));
+        b = min(max(b, 0), nb - 1);
+        key = key * (unsigned)nb + (unsigned)b;
+    }
+    keys[t] = key;
+    idx[t] = (unsigned)p;
+}
+
+// particles a warp takes per visit of the work counter: 32 when the list keeps every warp busy for several visits,
+// fewer for short lists (so that they still spread over the SMs)
+static int scatter_chunk(long long n_list, int blocks)
+{
+    const long long warps = (long long)blocks * 8;
+    if (n_list >= 4 * 32 * warps) return 32;
+    if (n_list >= 4 * 8 * warps) return 8;
+    return 4;
+}
+
+static int order_list_2d(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int** list, long long n_list)
+{
+    const char* e_ord = getenv("S2G_2D_ORDER");
+    const long long image_bytes = G.npix * G.npix * 8LL * (G.n_images + 1);
+    if ((e_ord && atoi(e_ord) == 0) || n_list < 65536 || n_list >= (1LL << 31) || image_bytes < (48LL << 20)) return S2G_OK;
+    void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
+    S2G_TRY(s2g_scratch(ctx, "o2_keys", sizeof(unsigned) * n_list, &d_k));
+    S2G_TRY(s2g_scratch(ctx, "o2_keys2", sizeof(unsigned) * n_list, &d_k2));
+    S2G_TRY(s2g_scratch(ctx, "o2_idx", sizeof(unsigned) * n_list, &d_i));
+    S2G_TRY(s2g_scratch(ctx, "o2_idx2", sizeof(unsigned) * n_list, &d_i2));
+    const int nb = (int)((G.npix + 63) / 64);
+    k_order2d_keys<<<(int)((n_list + 255) / 256), 256, 0, ctx->stream>>>(P, G, *list, n_list, nb, (unsigned*)d_k,
+                                                                           (unsigned*)d_i);
+    S2G_CUDA(cudaGetLastError());
+    int bits = 1;
+    while ((1LL << bits) < (long long)nb * nb) ++bits;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                    (unsigned*)d_i2, (int)n_list, 0, bits, ctx->stream);
+    S2G_TRY(s2g_scratch(ctx, "o2_sort_tmp", sb + 16, &d_tmp));
+    S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                             (unsigned*)d_i2, (int)n_list, 0, bits, ctx->stream));
+    ctx->launches += 4;
+    *list = (const int*)d_i2;   // particle indices are below 2^31 (s2g_particles.n is checked at the boundary)
+    return S2G_OK;
+}
+
 template <int KID>
 static int launch_scatter2d_sub_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const int* list,
                                   long long n_list, double* image)
 {
     if (n_list <= 0) return S2G_OK;
+    S2G_TRY(order_list_2d(ctx, P, G, &list, n_list));
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const long long warps_needed = std::min<long long>((n_list + 15) / 16, (long long)ctx->sm_count * 8 * 8);
     int blocks = (int)std::max<long long>(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
-    k_scatter2d_sub<KID, 8><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters);
+    k_scatter2d_sub<KID, 8><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters,
+                                                             scatter_chunk(n_list, blocks));
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return S2G_OK;
@@ -320,11 +577,13 @@ static int launch_scatter2d_k(s2g_ctx* ctx, const s2g_particles& P, const s2g_ge
                               long long n_list, double* image)
 {
     if (n_list <= 0) return S2G_OK;
+    S2G_TRY(order_list_2d(ctx, P, G, &list, n_list));
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     const int warps_needed = (int)std::min<long long>((n_list + 3) / 4, (long long)ctx->sm_count * 8 * 8);
     int blocks = max(1, (warps_needed + 7) / 8);
     blocks = min(blocks, ctx->sm_count * 8);
-    k_scatter2d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters);
+    k_scatter2d<KID><<<blocks, 256, 0, ctx->stream>>>(P, G, list, n_list, image, ctx->d_counters,
+                                                      scatter_chunk(n_list, blocks));
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return S2G_OK;

@@ -1,4 +1,7 @@
 // s2g_misc.cu — CIC/TSC stencils, finite-guarded accumulate, synthetic particle stream, roofline microbenchmarks.
+#include <cub/cub.cuh>
+#include <cstdlib>
+
 #include "s2g_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -9,10 +12,12 @@
 template <int ORDER, int DIMS>
 __global__ void __launch_bounds__(256) k_stencil(const void* __restrict__ pos, const void* __restrict__ q, long long n,
                                                  int in_dtype, double len2pix, double half_n, long long npix,
-                                                 int periodic, double* __restrict__ image)
+                                                 int periodic, double* __restrict__ image,
+                                                 const unsigned* __restrict__ order)
 {
-    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long p = order ? (long long)order[t] : t;
     const long long ncell = DIMS == 2 ? npix * npix : npix * npix * npix;
     double wgt[3][3];
     long long c0[3];
@@ -75,20 +80,69 @@ __global__ void __launch_bounds__(256) k_stencil(const void* __restrict__ pos, c
     }
 }
 
+// Deposit order: by the block (16^3 cells, 64^2 pixels) of the particle position.  A thread's reds go to its own cells —
+// in input order every one of them misses L2 once the grid is larger than L2 (a DRAM sector read and written per
+// 2-3-cell row); in block order the threads in flight update one compact region.  S2G_STENCIL_ORDER=0: off.
+__global__ void __launch_bounds__(256) k_stencil_keys(const void* __restrict__ pos, long long n, int in_dtype, int dims,
+                                                      double len2pix, double half_n, int nb, double inv_block,
+                                                      unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned key = 0;
+    for (int d = 0; d < dims; ++d) {
+        const double g = fma(ld_in(pos, 3 * p + d, in_dtype), len2pix, half_n);
+        int b = (g == g) ? (int)floor(fmin(fmax(g * inv_block, -1.0), (double)nb)) : 0;
+        b = min(max(b, 0), nb - 1);
+        key = key * (unsigned)nb + (unsigned)b;
+    }
+    keys[p] = key;
+    idx[p] = (unsigned)p;
+}
+
 int s2g_launch_stencil(s2g_ctx* ctx, int order, int dims, const void* pos, const void* q, long long n, int in_dtype,
                        double len2pix, long long npix, int periodic, double* image)
 {
     if (n <= 0) return S2G_OK;
     const int blocks = (int)((n + 255) / 256);
     const double half_n = 0.5 * (double)npix;
+    const unsigned* ord = nullptr;
+    const char* e_ord = getenv("S2G_STENCIL_ORDER");
+    const long long grid_bytes = 16LL * (dims == 2 ? npix * npix : npix * npix * npix);
+    if (!(e_ord && atoi(e_ord) == 0) && n >= 65536 && n < (1LL << 31) && grid_bytes > (48LL << 20)) {
+        const int bs = dims == 2 ? 64 : 16;
+        const int nb = (int)((npix + bs - 1) / bs);
+        void *d_k, *d_k2, *d_i, *d_i2, *d_tmp;
+        S2G_TRY(s2g_scratch(ctx, "st_keys", sizeof(unsigned) * n, &d_k));
+        S2G_TRY(s2g_scratch(ctx, "st_keys2", sizeof(unsigned) * n, &d_k2));
+        S2G_TRY(s2g_scratch(ctx, "st_idx", sizeof(unsigned) * n, &d_i));
+        S2G_TRY(s2g_scratch(ctx, "st_idx2", sizeof(unsigned) * n, &d_i2));
+        k_stencil_keys<<<blocks, 256, 0, ctx->stream>>>(pos, n, in_dtype, dims, len2pix, half_n, nb, 1.0 / bs,
+                                                        (unsigned*)d_k, (unsigned*)d_i);
+        S2G_CUDA(cudaGetLastError());
+        long long nkeys = 1;
+        for (int d = 0; d < dims; ++d) nkeys *= nb;
+        int bits = 1;
+        while ((1LL << bits) < nkeys) ++bits;
+        if (bits <= 32) {
+            size_t sb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, sb, (const unsigned*)d_k, (unsigned*)d_k2, (const unsigned*)d_i,
+                                            (unsigned*)d_i2, (int)n, 0, bits, ctx->stream);
+            S2G_TRY(s2g_scratch(ctx, "st_sort_tmp", sb + 16, &d_tmp));
+            S2G_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sb, (const unsigned*)d_k, (unsigned*)d_k2,
+                                                     (const unsigned*)d_i, (unsigned*)d_i2, (int)n, 0, bits, ctx->stream));
+            ctx->launches += 4;
+            ord = (const unsigned*)d_i2;
+        }
+    }
     if (order == 2 && dims == 2)
-        k_stencil<2, 2><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image);
+        k_stencil<2, 2><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image, ord);
     else if (order == 2 && dims == 3)
-        k_stencil<2, 3><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image);
+        k_stencil<2, 3><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image, ord);
     else if (order == 3 && dims == 2)
-        k_stencil<3, 2><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image);
+        k_stencil<3, 2><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image, ord);
     else
-        k_stencil<3, 3><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image);
+        k_stencil<3, 3><<<blocks, 256, 0, ctx->stream>>>(pos, q, n, in_dtype, len2pix, half_n, npix, periodic, image, ord);
     S2G_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return S2G_OK;
