@@ -67,7 +67,7 @@ SIGMA = 1.5
 KERNEL_DIM = {2: 2, 3: 3, 0: 2}
 HP_SHELL = (0.05, 0.5)
 # the other BASELINE configs carried by the default run: (workload, steps, warm-up)
-EXTRAS = [("c3", 3, 2), ("c3cic", 3, 2), ("c3tsc", 3, 2), ("c4", 1, 1), ("c5", 1, 1)]
+EXTRAS = [("c3", 3, 2), ("c3cic", 3, 2), ("c3tsc", 3, 2), ("tiny", 3, 2), ("c4", 1, 1), ("c5", 1, 1)]
 # particles of the stream the parity check / CPU baseline run on: (main workload, extra entry)
 PARITY_SAMPLE = {2: (1 << 17, 1 << 15), 3: (1 << 20, 1 << 18), 0: (1 << 16, 1 << 13), "stencil": (1 << 22, 1 << 20)}
 CPU_SAMPLE = {2: 1 << 19, 3: 1 << 20, 0: 1 << 16, "stencil": 1 << 24}

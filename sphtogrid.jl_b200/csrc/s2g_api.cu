@@ -345,23 +345,29 @@ static s2g_geom make_geom(double len2pix, int64_t npix, int n_images, int calc_m
 #include <thread>
 
 struct s2g_stager {
-    std::thread th;
+    // K helper threads (S2G_STAGE_THREADS, default 4): thread k stages the chunks k, k + K, ... on its own copy stream
+    // through its own pinned bounce buffers.  One thread's memcpy() into the bounce buffer runs at ~10 GB/s — a third
+    // of what the PCIe link takes — so the threads fill the link together.
+    static constexpr int MAXT = 8;
+    static constexpr int NBOUNCE = 3;
+    static constexpr size_t BOUNCE_BYTES = 4u << 20;
+    int nthreads = 0;
+    std::thread th[MAXT];
     std::mutex mu;
     std::condition_variable cv;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream[MAXT] = {};
     cudaEvent_t start_ev = nullptr;
-    // own pinned bounce buffers: the helper thread memcpy()s a piece of the caller's (pageable) array into one of them
+    // own pinned bounce buffers: a helper thread memcpy()s a piece of the caller's (pageable) array into one of them
     // and issues a truly asynchronous copy from there.  A pageable cudaMemcpyAsync instead holds the driver while it
     // stages the data, which delayed the kernel launches of the calling thread (measured: +45 ms per C2 map).
-    static constexpr int NBOUNCE = 3;
-    static constexpr size_t BOUNCE_BYTES = 8u << 20;
-    void* bounce[NBOUNCE] = {nullptr, nullptr, nullptr};
-    cudaEvent_t bounce_ev[NBOUNCE] = {nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> ev;
-    long long chunk = 1 << 20;   // particles per chunk
+    void* bounce[MAXT][NBOUNCE] = {};
+    cudaEvent_t bounce_ev[MAXT][NBOUNCE] = {};
+    std::vector<cudaEvent_t> ev;   // one per chunk, recorded on the stream of the thread that staged it
+    std::vector<char> done;        // chunk's event has been recorded
+    long long chunk = 1 << 20;     // particles per chunk
     long long n = 0;
-    int recorded = 0;            // chunks whose event has been recorded
-    int error = 0;               // cudaError_t of the helper thread
+    int recorded = 0;              // length of the prefix of chunks whose events have been recorded
+    int error = 0;                 // first cudaError_t of a helper thread
     bool active = false;
 };
 
@@ -369,7 +375,8 @@ static void stager_join(s2g_ctx* ctx)
 {
     s2g_stager* s = ctx->stager;
     if (!s) return;
-    if (s->th.joinable()) s->th.join();
+    for (int k = 0; k < s2g_stager::MAXT; ++k)
+        if (s->th[k].joinable()) s->th[k].join();
     s->active = false;
 }
 
@@ -399,11 +406,13 @@ static void stager_destroy(s2g_ctx* ctx)
     stager_join(ctx);
     for (auto e : s->ev) cudaEventDestroy(e);
     if (s->start_ev) cudaEventDestroy(s->start_ev);
-    for (int b = 0; b < s2g_stager::NBOUNCE; ++b) {
-        if (s->bounce[b]) cudaFreeHost(s->bounce[b]);
-        if (s->bounce_ev[b]) cudaEventDestroy(s->bounce_ev[b]);
+    for (int k = 0; k < s2g_stager::MAXT; ++k) {
+        for (int b = 0; b < s2g_stager::NBOUNCE; ++b) {
+            if (s->bounce[k][b]) cudaFreeHost(s->bounce[k][b]);
+            if (s->bounce_ev[k][b]) cudaEventDestroy(s->bounce_ev[k][b]);
+        }
+        if (s->copy_stream[k]) cudaStreamDestroy(s->copy_stream[k]);
     }
-    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
     ctx->stager = nullptr;
 }
@@ -423,7 +432,11 @@ int s2g_stage_wait(s2g_ctx* ctx, long long upto)
             return S2G_ECUDA;
         }
     }
-    S2G_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[(size_t)c], 0));
+    // the last chunk <= c of every helper thread (a thread's stream is in order: it covers the thread's earlier chunks)
+    for (int k = 0; k < s->nthreads; ++k) {
+        const int ck = c - ((c - k) % s->nthreads + s->nthreads) % s->nthreads;
+        if (ck >= 0) S2G_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev[(size_t)ck], 0));
+    }
     return S2G_OK;
 }
 
@@ -450,19 +463,25 @@ static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, cons
     long long stage_min = 2 << 20;   // particles from which the helper thread pays off (S2G_STAGE_MIN: tests lower it)
     if (const char* e = getenv("S2G_STAGE_MIN")) stage_min = atoll(e);
     if (n > stage_min && !overlap_off) {
-        // helper thread: chunks of 1 Mi particles, all six arrays of a chunk, then the chunk's event
+        // helper threads: chunks of 1 Mi particles, all six arrays of a chunk, then the chunk's event
         if (!ctx->stager) {
             ctx->stager = new s2g_stager();
+            s2g_stager* s0 = ctx->stager;
             if (const char* e = getenv("S2G_STAGE_CHUNK")) {
                 const long long c = atoll(e);
-                if (c >= 1024) ctx->stager->chunk = c;
+                if (c >= 1024) s0->chunk = c;
             }
-            S2G_CUDA(cudaStreamCreateWithFlags(&ctx->stager->copy_stream, cudaStreamNonBlocking));
-            S2G_CUDA(cudaEventCreateWithFlags(&ctx->stager->start_ev, cudaEventDisableTiming));
+            int nt = 4;
+            if (const char* e = getenv("S2G_STAGE_THREADS")) nt = atoi(e);
+            s0->nthreads = std::min(std::max(nt, 1), (int)s2g_stager::MAXT);
+            S2G_CUDA(cudaEventCreateWithFlags(&s0->start_ev, cudaEventDisableTiming));
             const bool bounce_off = getenv("S2G_STAGE_BOUNCE") && atoi(getenv("S2G_STAGE_BOUNCE")) == 0;
-            for (int b = 0; b < s2g_stager::NBOUNCE && !bounce_off; ++b) {
-                S2G_CUDA(cudaMallocHost(&ctx->stager->bounce[b], s2g_stager::BOUNCE_BYTES));
-                S2G_CUDA(cudaEventCreateWithFlags(&ctx->stager->bounce_ev[b], cudaEventDisableTiming));
+            for (int k = 0; k < s0->nthreads; ++k) {
+                S2G_CUDA(cudaStreamCreateWithFlags(&s0->copy_stream[k], cudaStreamNonBlocking));
+                for (int b = 0; b < s2g_stager::NBOUNCE && !bounce_off; ++b) {
+                    S2G_CUDA(cudaMallocHost(&s0->bounce[k][b], s2g_stager::BOUNCE_BYTES));
+                    S2G_CUDA(cudaEventCreateWithFlags(&s0->bounce_ev[k][b], cudaEventDisableTiming));
+                }
             }
         }
         s2g_stager* s = ctx->stager;
@@ -473,18 +492,23 @@ static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, cons
             S2G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             s->ev.push_back(e);
         }
+        s->done.assign((size_t)nchunks, 0);
         // the device buffers may still be read by work of the previous call on ctx->stream
         S2G_CUDA(cudaEventRecord(s->start_ev, ctx->stream));
-        S2G_CUDA(cudaStreamWaitEvent(s->copy_stream, s->start_ev, 0));
+        for (int k = 0; k < s->nthreads; ++k) S2G_CUDA(cudaStreamWaitEvent(s->copy_stream[k], s->start_ev, 0));
         s->n = n; s->recorded = 0; s->error = 0; s->active = true;
         const int device = ctx->device;
         const size_t nim = (size_t)n_images;
+        const int K = s->nthreads;
+        int started = 0;
         try {
-        s->th = std::thread([=]() {
+        for (int k = 0; k < K; ++k) {
+        s->th[k] = std::thread([=]() {
             cudaSetDevice(device);
+            cudaStream_t cs = s->copy_stream[k];
             unsigned long long bounce_turn = 0;
             bool bounce_used[s2g_stager::NBOUNCE] = {false, false, false};
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = k; c < nchunks; c += K) {
                 const size_t o = (size_t)c * (size_t)s->chunk;
                 const size_t cnt = std::min<size_t>((size_t)s->chunk, (size_t)n - o);
                 cudaError_t e = cudaSuccess;
@@ -492,36 +516,46 @@ static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, cons
                     char* dst = (char*)d + o * per * es;
                     const char* src = (const char*)h + o * per * es;
                     size_t left = cnt * per * es;
-                    if (!s->bounce[0]) {   // no bounce buffers: the driver's pageable path
-                        if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, left, cudaMemcpyHostToDevice, s->copy_stream);
+                    if (!s->bounce[k][0]) {   // no bounce buffers: the driver's pageable path
+                        if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, left, cudaMemcpyHostToDevice, cs);
                         return;
                     }
                     while (left > 0 && e == cudaSuccess) {
                         const int b = (int)(bounce_turn++ % s2g_stager::NBOUNCE);
                         const size_t piece = std::min(left, s2g_stager::BOUNCE_BYTES);
-                        if (bounce_used[b]) e = cudaEventSynchronize(s->bounce_ev[b]);   // its previous DMA has read it
+                        if (bounce_used[b]) e = cudaEventSynchronize(s->bounce_ev[k][b]);   // its previous DMA has read it
                         if (e != cudaSuccess) break;
-                        memcpy(s->bounce[b], src, piece);
-                        e = cudaMemcpyAsync(dst, s->bounce[b], piece, cudaMemcpyHostToDevice, s->copy_stream);
-                        if (e == cudaSuccess) e = cudaEventRecord(s->bounce_ev[b], s->copy_stream);
+                        memcpy(s->bounce[k][b], src, piece);
+                        e = cudaMemcpyAsync(dst, s->bounce[k][b], piece, cudaMemcpyHostToDevice, cs);
+                        if (e == cudaSuccess) e = cudaEventRecord(s->bounce_ev[k][b], cs);
                         bounce_used[b] = true;
                         dst += piece; src += piece; left -= piece;
                     }
                 };
                 cp(dpos, pos, 3); cp(dh, hsml, 1); cp(dm, m, 1); cp(dr, rho, 1); cp(dq, binq, nim); cp(dw, w, 1);
-                if (e == cudaSuccess) e = cudaEventRecord(s->ev[(size_t)c], s->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(s->ev[(size_t)c], cs);
+                bool stop = false;
                 {
                     std::lock_guard<std::mutex> lk(s->mu);
-                    if (e != cudaSuccess) s->error = (int)e;
-                    s->recorded = c + 1;
+                    if (e != cudaSuccess && s->error == 0) s->error = (int)e;
+                    s->done[(size_t)c] = 1;
+                    while (s->recorded < nchunks && s->done[(size_t)s->recorded]) ++s->recorded;
+                    stop = s->error != 0;
                 }
                 s->cv.notify_all();
-                if (e != cudaSuccess) break;
+                if (stop) break;
             }
         });
+        ++started;
+        }
         threaded = true;
-        } catch (...) {   // no thread to be had: copy on the calling thread like a small input
-            s->active = false;
+        } catch (...) {   // no (further) thread to be had
+            if (started == 0)
+                s->active = false;   // copy on the calling thread like a small input
+            else {
+                // some threads run: let them finish, then fall back to the calling thread for everything
+                stager_join(ctx);
+            }
         }
     }
     if (!threaded && n > 0) {

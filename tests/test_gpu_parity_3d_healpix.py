@@ -388,3 +388,21 @@ def test_healpix_map_strict_reference_opt_out(s2g, oracle):
         ea, ew, est = oracle.healpix_deposit(d[keep], hsml[keep], m[keep], rho[keep], q[keep], w[keep], 64, "WendlandC4",
                                              2, calc_mean, n_workers=ncores(), exact="sens")
         assert_healpix_parity(a, wm, ea, ew, est, what=f"strict_reference=False calc_mean={calc_mean}")
+
+
+@pytest.mark.parametrize("order,dims,npix", [(2, 3, 160), (3, 3, 160), (2, 2, 2048), (3, 2, 2048)])
+def test_stencils_block_ordered_deposit(s2g, oracle, order, dims, npix, monkeypatch):
+    """CIC / TSC on a grid larger than L2's share (160^3 / 2048^2 cells x 2 planes >= 65 MB) with more than 65536
+    particles: the particles are deposited in the key order of their 16^3-cell (64^2-pixel) block (csrc/s2g_misc.cu,
+    k_stencil_keys + radix sort).  Against the oracle, periodic and clipped, and against the unordered deposit."""
+    pos, hsml, m, rho, q, w = random_particles(52, 150000, box=10.6)
+    pos[:50] = np.nan_to_num(pos[:50]) * 40.0            # far outside the box: clamped keys, clipped / wrapped cells
+    par = s2g.mappingParameters(center=[0, 0, 0], x_size=10.0, y_size=10.0, z_size=10.0, Npixels=npix)
+    fn = s2g.cic_deposit if order == 2 else s2g.tsc_deposit
+    for periodic in (False, True):
+        got = fn(pos, q, param=par, dimensions=dims, average=False, periodic=periodic)
+        ref = oracle.stencil_deposit(order, dims, pos, q, par.len2pix, npix, periodic)
+        assert_parity(got, ref, rtol=1e-12, what=f"ordered stencil order={order} dims={dims} periodic={periodic}")
+    monkeypatch.setenv("S2G_STENCIL_ORDER", "0")
+    plain = fn(pos, q, param=par, dimensions=dims, average=False, periodic=True)
+    assert_parity(got, plain, rtol=1e-12, what="stencil order on vs off")
