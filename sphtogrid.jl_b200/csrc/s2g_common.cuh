@@ -120,6 +120,7 @@ enum {
     CNT_SCATTER = 5,
     CNT_GATHER = 6,
     CNT_WORK = 7,  // dynamic work-queue cursor
+    CNT_AUX = 8,   // length of a device-built work list (k_norm2d_fast -> k_norm2d)
     CNT_N = 16
 };
 

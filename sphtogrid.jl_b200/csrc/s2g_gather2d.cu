@@ -204,19 +204,23 @@ __device__ __forceinline__ double pass_a_region(double x, double y, double h, do
 // dependency chains keep the FP64 pipe busy).  Unclipped, well-resolved footprints take the closed form
 // h²·∫w instead (analytic_norm_min_h).  Particles in the "no pixel centre covered" branch are re-routed to the
 // scatter kernel (they are tiny or clipped; their wk := 1 deposit does not fit the gather kernel's inner loop).
+// `slow` (optional): the entries of `list` the warp kernel still has to do, *n_slow of them (built by k_norm2d_fast).
 template <int KID>
 __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, const int* __restrict__ list,
                                                 long long n_list, int exact_norm, GRec* __restrict__ recs,
                                                 unsigned* __restrict__ npairs_g, int* __restrict__ reroute,
-                                                unsigned long long* __restrict__ counters)
+                                                unsigned long long* __restrict__ counters,
+                                                const unsigned* __restrict__ slow)
 {
     const int lane = threadIdx.x & 31;
     unsigned long long mapped = 0, fpx = 0;
+    const long long n_work = slow ? (long long)counters[CNT_AUX] : n_list;
     for (;;) {
         long long t = 0;
         if (lane == 0) t = (long long)atomicAdd(&counters[CNT_WORK], 1ull);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_list) break;
+        if (t >= n_work) break;
+        if (slow) t = (long long)slow[t];
         const long long p = list[t];
         Rec2 r;
         make_rec2(P, G, p, r);  // known valid
@@ -292,6 +296,71 @@ __global__ void __launch_bounds__(256) k_norm2d(s2g_particles P, s2g_geom G, con
     if (lane == 0) {
         if (mapped) { atomicAdd(&counters[CNT_MAPPED], mapped); atomicAdd(&counters[CNT_GATHER], mapped); }
         if (fpx) atomicAdd(&counters[CNT_FOOTPRINT], fpx);
+    }
+}
+
+// ---- pass A, one THREAD per particle, for what needs no sum: an unclipped footprint resolved well enough for the closed
+// form (the bulk of a gather class).  The record, the normalisation and the tile count are the per-particle arithmetic
+// of k_norm2d's closed-form branch, bit for bit; a warp per particle left 31 lanes idle there and paid one memory
+// latency per particle (C5: 2.7 s of a 25.8-s map).  Everything else — clipped, under-resolved, degenerate — is
+// appended to `slow` for the warp kernel.
+template <int KID>
+__global__ void __launch_bounds__(256) k_norm2d_fast(s2g_particles P, s2g_geom G, const int* __restrict__ list,
+                                                     long long n_list, GRec* __restrict__ recs,
+                                                     unsigned* __restrict__ npairs_g, unsigned* __restrict__ slow,
+                                                     unsigned long long* __restrict__ counters)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool is_slow = false;
+    unsigned long long mapped = 0, fpx = 0;
+    if (t < n_list) {
+        const long long p = list[t];
+        Rec2 r;
+        make_rec2(P, G, p, r);  // known valid
+        const int n1 = (int)G.npix - 1;
+        const bool unclipped = floor_to_int(r.x - r.h) >= 0 && floor_to_int(r.x + r.h) <= n1 &&
+                               floor_to_int(r.y - r.h) >= 0 && floor_to_int(r.y + r.h) <= n1;
+        const bool resolved = r.h >= analytic_norm_min_h(KID);
+        const double sw = r.h * r.h * shape_integral_2d(KID);
+        const double an_probe = (r.area / sw) * r.w * r.dz;
+        if (!(resolved && unclipped) || sw == 0.0 || !isfinite(an_probe)) {
+            is_slow = true;
+        } else {
+            GRec g;
+            g.x = r.x; g.y = r.y; g.h = r.h; g.hinv = r.hinv;
+            g.dx_lo = overlap_1d(r.x, r.h, r.iMin); g.dx_hi = overlap_1d(r.x, r.h, r.iMax);
+            g.dy_lo = overlap_1d(r.y, r.h, r.jMin); g.dy_hi = overlap_1d(r.y, r.h, r.jMax);
+            g.iMin = r.iMin; g.iMax = r.iMax; g.jMin = r.jMin; g.jMax = r.jMax;
+            g.p = (int)p;
+            g.f32_ok = 1;
+            const double n_distr = 1.0;
+            const double kernel_norm = r.area / n_distr;
+            g.an = kernel_norm * (n_distr / sw) * r.w * r.dz;
+            const int ti0 = r.iMin / TILE_H, ti1 = r.iMax / TILE_H, tj0 = r.jMin / TILE_W, tj1 = r.jMax / TILE_W;
+            unsigned np = 0;
+            for (int ti = ti0; ti <= ti1; ++ti)
+                for (int tj = tj0; tj <= tj1; ++tj)
+                    if (tile_hit(g, ti, tj)) ++np;
+            recs[t] = g;
+            npairs_g[t] = np;
+            mapped = 1;
+            fpx = (unsigned long long)(r.iMax - r.iMin + 1) * (unsigned long long)(r.jMax - r.jMin + 1);
+        }
+    }
+    const unsigned sm = __ballot_sync(0xffffffffu, is_slow);
+    if (sm) {
+        unsigned long long base = 0;
+        if (lane == __ffs(sm) - 1) base = atomicAdd(&counters[CNT_AUX], (unsigned long long)__popc(sm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(sm) - 1);
+        if (is_slow) slow[base + __popc(sm & ((1u << lane) - 1u))] = (unsigned)t;
+    }
+    mapped = (unsigned long long)warp_sum_ll((long long)mapped);
+    fpx = (unsigned long long)warp_sum_ll((long long)fpx);
+    if (lane == 0 && mapped) {
+        atomicAdd(&counters[CNT_MAPPED], mapped);
+        atomicAdd(&counters[CNT_GATHER], mapped);
+        atomicAdd(&counters[CNT_FOOTPRINT], fpx);
     }
 }
 
@@ -612,9 +681,21 @@ int launch_norm(s2g_ctx* ctx, const s2g_particles& P, const s2g_geom& G, const i
 {
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_WORK, 0, sizeof(unsigned long long), ctx->stream));
     S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_PAIRS, 0, sizeof(unsigned long long), ctx->stream));
+    const unsigned* slow = nullptr;
+    if (!exact_norm && analytic_norm_min_h(KID) < 1e200 && n_list > 0) {
+        // thread per particle for the closed-form particles; the warp kernel does the listed rest
+        void* d_slow;
+        S2G_TRY(s2g_scratch(ctx, "g_slow", sizeof(unsigned) * (size_t)n_list, &d_slow));
+        S2G_CUDA(cudaMemsetAsync(ctx->d_counters + CNT_AUX, 0, sizeof(unsigned long long), ctx->stream));
+        k_norm2d_fast<KID><<<(int)((n_list + 255) / 256), 256, 0, ctx->stream>>>(P, G, list, n_list, recs, npairs_g,
+                                                                                  (unsigned*)d_slow, ctx->d_counters);
+        S2G_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        slow = (const unsigned*)d_slow;
+    }
     const int blocks = (int)std::min<long long>((n_list + 7) / 8, (long long)ctx->sm_count * 8);
     k_norm2d<KID><<<max(blocks, 1), 256, 0, ctx->stream>>>(P, G, list, n_list, exact_norm, recs, npairs_g, reroute,
-                                                          ctx->d_counters);
+                                                          ctx->d_counters, slow);
     S2G_CUDA(cudaGetLastError());
     return S2G_OK;
 }
