@@ -445,6 +445,79 @@ long long s2g_stage_first_slice(const s2g_ctx* ctx)
     return (ctx->stager && ctx->stager->active) ? ctx->stager->chunk : 0;
 }
 
+// Result map back to the caller's (pageable) array.  A pageable device->host cudaMemcpyAsync goes through the driver's
+// staging at ~11 GB/s (the 1.07-GB grid of BASELINE config 3: ~95 ms); here the helper threads of the stager copy
+// 4-MB pieces into their pinned bounce buffers on their own streams (up to three in flight per thread) and memcpy()
+// them out, several at a time.  Used for results of at least S2G_UNSTAGE_MIN bytes (default 32 MB) when the context
+// has a stager with bounce buffers (i.e. a large input came in through it); returns when `dst` is complete.
+static int unstage_output(s2g_ctx* ctx, void* dst, const void* src_dev, size_t bytes)
+{
+    size_t min_bytes = (size_t)32 << 20;
+    if (const char* e = getenv("S2G_UNSTAGE_MIN")) min_bytes = (size_t)atoll(e);
+    s2g_stager* s = ctx->stager;
+    bool plain = !s || s->nthreads <= 0 || !s->bounce[0][0] || bytes < min_bytes || bytes == 0;
+    if (!plain) {   // a pinned (or registered) destination takes the direct copy at link speed
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) plain = at.type != cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (plain) {
+        if (bytes > 0) S2G_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return S2G_OK;
+    }
+    S2G_TRY(stager_finish(ctx));   // the input copies are long done; the threads and buffers are free
+    S2G_CUDA(cudaEventRecord(s->start_ev, ctx->stream));
+    for (int k = 0; k < s->nthreads; ++k) S2G_CUDA(cudaStreamWaitEvent(s->copy_stream[k], s->start_ev, 0));
+    const size_t piece = s2g_stager::BOUNCE_BYTES;
+    const size_t npieces = (bytes + piece - 1) / piece;
+    const int K = s->nthreads, device = ctx->device;
+    int errs[s2g_stager::MAXT] = {};
+    int started = 0;
+    try {
+        for (int k = 0; k < K; ++k) {
+            s->th[k] = std::thread([=, &errs]() {
+                cudaSetDevice(device);
+                cudaStream_t cs = s->copy_stream[k];
+                size_t off_of[s2g_stager::NBOUNCE] = {}, len_of[s2g_stager::NBOUNCE] = {};
+                bool used[s2g_stager::NBOUNCE] = {};
+                cudaError_t e = cudaSuccess;
+                unsigned long long turn = 0;
+                auto drain = [&](int b) {
+                    if (!used[b] || e != cudaSuccess) return;
+                    e = cudaEventSynchronize(s->bounce_ev[k][b]);
+                    if (e == cudaSuccess) memcpy((char*)dst + off_of[b], s->bounce[k][b], len_of[b]);
+                    used[b] = false;
+                };
+                for (size_t i = (size_t)k; i < npieces && e == cudaSuccess; i += (size_t)K) {
+                    const int b = (int)(turn++ % s2g_stager::NBOUNCE);
+                    drain(b);
+                    if (e != cudaSuccess) break;
+                    const size_t off = i * piece, len = std::min(piece, bytes - off);
+                    e = cudaMemcpyAsync(s->bounce[k][b], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, cs);
+                    if (e == cudaSuccess) e = cudaEventRecord(s->bounce_ev[k][b], cs);
+                    off_of[b] = off; len_of[b] = len; used[b] = (e == cudaSuccess);
+                }
+                for (int j = 0; j < s2g_stager::NBOUNCE; ++j) drain((int)((turn + j) % s2g_stager::NBOUNCE));   // oldest first
+                errs[k] = (int)e;
+            });
+            ++started;
+        }
+    } catch (...) {
+    }
+    for (int k = 0; k < s2g_stager::MAXT; ++k)
+        if (s->th[k].joinable()) s->th[k].join();
+    if (started < K) {   // not every piece had a thread: redo the whole copy the plain way
+        S2G_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return S2G_OK;
+    }
+    for (int k = 0; k < K; ++k)
+        if (errs[k] != 0) {
+            s2g_set_error("device->host copy of the result failed: %s", cudaGetErrorString((cudaError_t)errs[k]));
+            return S2G_ECUDA;
+        }
+    return S2G_OK;
+}
+
 // copies the six host arrays into scratch device buffers
 static int stage_particles(s2g_ctx* ctx, const void* pos, const void* hsml, const void* m, const void* rho,
                            const void* binq, const void* w, int64_t n, int n_images, int in_dtype, s2g_particles& P)
@@ -1017,7 +1090,7 @@ static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* p
     const bool both = dims == 2 && return_both_maps;
     if (both) {
         S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-        S2G_CUDA(cudaMemcpyAsync(out, dimg, sizeof(double) * ncell * planes, cudaMemcpyDeviceToHost, ctx->stream));
+        S2G_TRY(unstage_output(ctx, out, dimg, sizeof(double) * ncell * planes));
     } else {
         void* dred = nullptr;
         S2G_TRY(s2g_scratch(ctx, "reduced", sizeof(double) * ncell * out_planes, &dred));
@@ -1026,7 +1099,7 @@ static int sphmap_impl(const char* fn, s2g_ctx* ctx, int32_t dims, const void* p
         else
             S2G_TRY(s2g_launch_reduce_3d(ctx, (const double*)dimg, npix, reduce_image, (double*)dred));
         S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-        S2G_CUDA(cudaMemcpyAsync(out, dred, sizeof(double) * ncell * out_planes, cudaMemcpyDeviceToHost, ctx->stream));
+        S2G_TRY(unstage_output(ctx, out, dred, sizeof(double) * ncell * out_planes));
     }
     S2G_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     S2G_TRY(stats_collect(ctx));
@@ -1206,8 +1279,8 @@ extern "C" int s2g_healpix_map(s2g_ctx* ctx, const void* pos, const void* hsml, 
     S2G_TRY(s2g_healpix_stage_deposit(__func__, ctx, pos, hsml, m, rho, binq, w, n, center, radius_limits, nside,
                                       kernel, calc_mean, pos_recentred_out, &dmap, &nsel));
     const size_t npix = (size_t)(12 * nside * nside);
-    S2G_CUDA(cudaMemcpyAsync(map_out, dmap, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
-    S2G_CUDA(cudaMemcpyAsync(wmap_out, dmap + npix, sizeof(double) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    S2G_TRY(unstage_output(ctx, map_out, dmap, sizeof(double) * npix));
+    S2G_TRY(unstage_output(ctx, wmap_out, dmap + npix, sizeof(double) * npix));
     S2G_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     S2G_TRY(stats_collect(ctx));
     ctx->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);

@@ -366,3 +366,27 @@ def test_scatter_classes_block_order_and_record_board(s2g, oracle, kernel, monke
     plain = s2g.cic_mapping_2D(pos, hsml, m, rho, q, w, param=par, kernel=kern(s2g, kernel), calc_mean=True, ctx=ctx)
     assert_parity(got, plain, rtol=1e-12, what="block order on vs off")
     ctx.close()
+
+
+@pytest.mark.parametrize("both", [False, True])
+def test_result_map_copied_back_by_the_staging_threads(s2g, oracle, both, monkeypatch):
+    """A large result map goes back to the caller's pageable array through the staging threads' pinned bounce buffers
+    (unstage_output, csrc/s2g_api.cu): 4-MB pieces, several threads, up to three copies in flight per thread.  The
+    thresholds are lowered so that a 1536^2 map (19 MB = 5 pieces; 38 MB with return_both_maps) takes that path; the map
+    must be the oracle's, and identical to the one the plain copy returns."""
+    monkeypatch.setenv("S2G_STAGE_MIN", "1000")
+    monkeypatch.setenv("S2G_STAGE_CHUNK", "4096")
+    monkeypatch.setenv("S2G_UNSTAGE_MIN", "65536")
+    ctx = s2g.Context(0)
+    pos, hsml, m, rho, q, w = random_particles(81, 30000, box=6.5, hmin=0.005, hmax=0.05, center=3.0)
+    kw = dict(center=[3.0, 3.0, 3.0], x_size=6.0, y_size=6.0, z_size=6.0, Npixels=1536)
+    got = s2g.sphMapping(pos.copy(), hsml, m, rho, q, w, param=s2g.mappingParameters(**kw), kernel=s2g.WendlandC4(2),
+                         calc_mean=True, show_progress=False, ctx=ctx, return_both_maps=both)
+    ref = oracle.sph_mapping(pos.copy(), hsml, m, rho, q, w, param=oracle.mapping_parameters(**kw), kernel="WendlandC4",
+                             calc_mean=True, return_both_maps=both)
+    assert_parity(got, ref, what=f"threaded result copy, return_both_maps={both}")
+    monkeypatch.setenv("S2G_UNSTAGE_MIN", str(1 << 40))
+    plain = s2g.sphMapping(pos.copy(), hsml, m, rho, q, w, param=s2g.mappingParameters(**kw), kernel=s2g.WendlandC4(2),
+                           calc_mean=True, show_progress=False, ctx=ctx, return_both_maps=both)
+    assert_parity(got, plain, rtol=1e-12, what="threaded vs plain result copy")
+    ctx.close()
