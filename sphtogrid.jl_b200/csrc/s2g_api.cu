@@ -1065,8 +1065,8 @@ int s2g_sphmap_stage_deposit(const char* fn, s2g_ctx* ctx, int32_t dims, const v
         void* dpo;
         S2G_TRY(s2g_scratch(ctx, "pos_out", 3 * (size_t)n * esize(in_dtype), &dpo));
         S2G_TRY(s2g_launch_center_filter(ctx, P, dpo, nullptr));
-        S2G_CUDA(cudaMemcpyAsync(pos_recentred_out, dpo, 3 * (size_t)n * esize(in_dtype), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
+        // (in place for a Julia caller: unstage_output first joins the threads that were reading the same array)
+        S2G_TRY(unstage_output(ctx, pos_recentred_out, dpo, 3 * (size_t)n * esize(in_dtype)));
     }
     *image_dev_out = (double*)dimg;
     return S2G_OK;
@@ -1260,8 +1260,7 @@ int s2g_healpix_stage_deposit(const char* fn, s2g_ctx* ctx, const void* pos, con
         void* dpo;
         S2G_TRY(s2g_scratch(ctx, "pos_out", 3 * (size_t)n * sizeof(double), &dpo));
         S2G_TRY(s2g_launch_center_filter(ctx, P, dpo, nullptr));
-        S2G_CUDA(cudaMemcpyAsync(pos_recentred_out, dpo, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
+        S2G_TRY(unstage_output(ctx, pos_recentred_out, dpo, 3 * (size_t)n * sizeof(double)));
     }
     *maps_dev_out = dmap;
     if (n_selected) *n_selected = nsel;
