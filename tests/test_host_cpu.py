@@ -252,3 +252,27 @@ def test_bench_reference_arm_contract():
                          "--warmup", "0", "--cpu-sample", "2048", "--workload", "small"], capture_output=True,
                         text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r2.returncode == 0 and not [l for l in r2.stdout.splitlines() if l.startswith("{")]
+
+
+def test_flattened_footprint_index_without_integer_division():
+    """csrc/s2g_cic2d.cu `unflatten`: (row, column) of a flattened footprint index e (column fastest, nj columns) from a
+    single-precision reciprocal and ONE correction step instead of an integer division.  Restated in numpy float32 with
+    the same operation order (float(e) + 0.5f, times fl(1/nj), round down, correct by one) and compared with divmod —
+    exhaustively over the kernels' domain (footprints up to 1024 pixels) and on random large arguments."""
+    def unflatten(e, nj):
+        inv = (np.float32(1.0) / nj.astype(np.float32)).astype(np.float32)
+        ir = np.floor((e.astype(np.float32) + np.float32(0.5)) * inv).astype(np.int64)
+        jc = e - ir * nj
+        lo, hi = jc < 0, jc >= nj
+        ir = ir - lo + hi
+        jc = jc + lo * nj - hi * nj
+        return ir, jc
+
+    nj, e = np.meshgrid(np.arange(1, 1025, dtype=np.int64), np.arange(0, 2048, dtype=np.int64), indexing="ij")
+    ir, jc = unflatten(e.ravel(), nj.ravel())
+    assert np.array_equal(ir, e.ravel() // nj.ravel()) and np.array_equal(jc, e.ravel() % nj.ravel())
+    rng = np.random.default_rng(5)
+    nj = rng.integers(1, 1 << 20, size=2_000_000)
+    e = rng.integers(0, 1 << 20, size=2_000_000)
+    ir, jc = unflatten(e, nj)
+    assert np.array_equal(ir, e // nj) and np.array_equal(jc, e % nj)
